@@ -1,0 +1,153 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes front-end of the CPU oracle (``liboracle.so``, built by ``make -C oracle``):
+a restatement of the reference's per-pivot loop (src/v4_cub_reduction.cu:219-380)
+and the synthetic LP generators.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s cpu_baseline / reference legs may import this package; the product
+path (``simplex_method_gpu_b200``) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+MAX_ITER, OPTIMUM, UNBOUNDED, THETA_OVERFLOW = 0, 1, 2, 3
+
+
+class _Result(C.Structure):
+    _fields_ = [("status", C.c_int), ("iterations", C.c_long), ("pivots", C.c_long), ("z", C.c_double)]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so in-tree (gcc, a few seconds)."""
+    srcs = [os.path.join(_HERE, f) for f in ("simplex_oracle.c", "simplex_oracle_impl.h", "simplex_oracle.h", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        for name, real in (("oracle_solve_f64", C.c_double), ("oracle_solve_f32", C.c_float)):
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, real, C.c_long, C.c_int,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(_Result)]
+        L.lpgen_u01.restype = C.c_double
+        L.lpgen_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        for name in ("lpgen_dense_f64", "lpgen_dense_f32"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_uint64]
+        L.lpgen_klee_minty_f64.restype = None
+        L.lpgen_klee_minty_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.lpgen_assignment_f64.restype = None
+        L.lpgen_assignment_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_uint64, C.c_void_p]
+        L.oracle_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+@dataclass
+class OracleSolution:
+    status: int
+    iterations: int
+    pivots: int
+    z: float
+    x_b: np.ndarray
+    b_ixs: np.ndarray
+    y: np.ndarray
+    trace_p: np.ndarray
+    trace_q: np.ndarray
+    gap_p: np.ndarray
+    gap_q: np.ndarray
+    Binv: np.ndarray | None = field(default=None, repr=False)
+
+    def x(self, n: int) -> np.ndarray:
+        """Full primal vector (non-basic variables are 0)."""
+        out = np.zeros(n, dtype=self.x_b.dtype)
+        out[self.b_ixs] = self.x_b
+        return out
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=None) -> OracleSolution:
+    """A: (m, n) array in Fortran (column-major) order, dtype float32/float64; slack block last."""
+    dt = np.dtype(A.dtype)
+    assert dt in (np.float32, np.float64)
+    A = np.asfortranarray(A, dtype=dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    c = np.ascontiguousarray(c, dtype=dt)
+    m, n = A.shape
+    cap = int(trace_cap if trace_cap is not None else min(max_iter, 1 << 22))
+    x_b = np.zeros(m, dt)
+    y = np.zeros(m, dt)
+    b_ixs = np.zeros(m, np.int32)
+    Binv = np.zeros((m, m), dt, order="F") if want_Binv else None
+    tp = np.full(cap, -1, np.int32)
+    tq = np.full(cap, -1, np.int32)
+    gp = np.zeros(cap, np.float64)
+    gq = np.zeros(cap, np.float64)
+    res = _Result()
+    fn = lib().oracle_solve_f64 if dt == np.float64 else lib().oracle_solve_f32
+    rc = fn(_ptr(A), _ptr(b), _ptr(c), m, n, eps, int(max_iter), int(order),
+            _ptr(x_b), _ptr(b_ixs), _ptr(y), _ptr(Binv), _ptr(tp), _ptr(tq), _ptr(gp), _ptr(gq), cap, C.byref(res))
+    if rc != 0:
+        raise ValueError(f"oracle_solve failed with code {rc} (m={m}, n={n})")
+    k = min(res.pivots, cap)
+    return OracleSolution(res.status, res.iterations, res.pivots, res.z, x_b, b_ixs, y,
+                          tp[:k], tq[:k], gp[:k], gq[:k], Binv)
+
+
+def gen_dense(m: int, n: int, seed: int = 1, dtype=np.float64):
+    dt = np.dtype(dtype)
+    A = np.empty((m, n), dt, order="F")
+    b = np.empty(m, dt)
+    c = np.empty(n, dt)
+    fn = lib().lpgen_dense_f64 if dt == np.float64 else lib().lpgen_dense_f32
+    fn(_ptr(A), _ptr(b), _ptr(c), m, n, seed)
+    return A, b, c
+
+
+def gen_klee_minty(d: int):
+    A = np.empty((d, 2 * d), np.float64, order="F")
+    b = np.empty(d, np.float64)
+    c = np.empty(2 * d, np.float64)
+    lib().lpgen_klee_minty_f64(_ptr(A), _ptr(b), _ptr(c), d)
+    return A, b, c
+
+
+def gen_assignment(k: int, seed: int = 1):
+    m, n = 2 * k, k * k + 2 * k
+    A = np.empty((m, n), np.float64, order="F")
+    b = np.empty(m, np.float64)
+    c = np.empty(n, np.float64)
+    w = np.empty(k * k, np.float64)
+    lib().lpgen_assignment_f64(_ptr(A), _ptr(b), _ptr(c), k, seed, _ptr(w))
+    return A, b, c, w.reshape(k, k)
+
+
+def u01(seed: int, stream: int, idx: int) -> float:
+    return lib().lpgen_u01(seed, stream, idx)
+
+
+def num_threads() -> int:
+    return lib().oracle_num_threads()

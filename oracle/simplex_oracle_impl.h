@@ -1,0 +1,282 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * CPU restatement of the per-pivot loop of the reference's revised simplex
+ * (reference: src/v4_cub_reduction.cu, "v4" below).  This header is included
+ * twice by simplex_oracle.c, once with REAL=float and once with REAL=double.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * legs may call it; the product path (simplex_method_gpu_b200/csrc) never does.
+ *
+ * What is followed, line by line:
+ *   initial state ........ v4:272-279  (B_inv = I, c_b = c[n-m..), x_b = b,
+ *                                      b_ixs[j] = n-m+j, y = c_b; the
+ *                                      `n - m` length at v4:277 is read as m,
+ *                                      the only length that fits y_aug)
+ *   pricing .............. v4:288-302  e = [1 y]·[-c; A] over ALL n columns,
+ *                                      argmin with lowest index on ties
+ *                                      (cub ArgMin), optimal iff min >= -EPS
+ *   FTRAN ................ v4:306-308  alpha = B_inv · A[:,p]
+ *   ratio test ........... v4:199-208, 311-326  eligibility alpha > 0 (strict),
+ *                                      theta = x_b/alpha else +INF, unbounded
+ *                                      iff no row is eligible, lowest index
+ *   row extract / E_q .... v4:331-332, 210-215 (row taken BEFORE the update;
+ *                                      the i==q entry is evaluated in double)
+ *   rank-1 update ........ v4:333      B_inv += E_q (x) row_q
+ *   bookkeeping .......... v4:339-342  c_b_q = c_b[q]; c_b[q] = c[p]; b_ixs[q] = p
+ *   x_b .................. v4:347-348  x_b += (row_q · b) E_q
+ *   y .................... v4:353-356  y += ((c_b_new · E_q) + (c_p - c_b_q)) row_q
+ *   loop / MAX_ITER ...... v4:286-287, 359
+ *   objective ............ v4:362-368  z = c_b · x_b
+ *
+ * cuBLAS does not document its summation order, so dot products / GEMV here
+ * use plain left-to-right fused multiply-adds.  `order` = 1 selects the
+ * summation order of the B200 engine instead (lane-strided partial sums and a
+ * butterfly, 256-column chunks for the FTRAN) so that engine results can be
+ * compared bit for bit; it changes nothing but the association of the sums.
+ */
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUFFIX)
+
+/* ---- dot products ---------------------------------------------------- */
+
+/* left-to-right fma chain starting from `init` */
+static REAL FN(dot_seq)(const REAL* x, const REAL* y, long n, REAL init) {
+	REAL acc = init;
+	for (long i = 0; i < n; ++i) acc = FMA(x[i], y[i], acc);
+	return acc;
+}
+
+/*
+ * Engine order for a length-n dot product done by one warp: lane l owns
+ * elements {k*32*V + l*V + v}, accumulates each v-slot in its own chain
+ * (V = 16 bytes / sizeof(REAL)), sums the slots left to right, then a
+ * butterfly (xor 16,8,4,2,1) over the 32 lanes.
+ */
+static REAL FN(dot_warp)(const REAL* x, const REAL* y, long n) {
+	enum { V = 16 / sizeof(REAL) };
+	REAL lane[32][V];
+	for (int l = 0; l < 32; ++l)
+		for (int v = 0; v < V; ++v) lane[l][v] = (REAL)0;
+	for (long base = 0; base < n; base += 32 * V)
+		for (int l = 0; l < 32; ++l)
+			for (int v = 0; v < V; ++v) {
+				long i = base + (long)l * V + v;
+				if (i < n) lane[l][v] = FMA(x[i], y[i], lane[l][v]);
+			}
+	REAL s[32];
+	for (int l = 0; l < 32; ++l) {
+		REAL a = lane[l][0];
+		for (int v = 1; v < V; ++v) a = a + lane[l][v];
+		s[l] = a;
+	}
+	for (int off = 16; off >= 1; off >>= 1) {
+		REAL t[32];
+		for (int l = 0; l < 32; ++l) t[l] = s[l] + s[l ^ off];
+		for (int l = 0; l < 32; ++l) s[l] = t[l];
+	}
+	return s[0];
+}
+
+/*
+ * Engine order for the O(m) bookkeeping dots: fixed slices of ORACLE_SLICE
+ * elements, each reduced by one 256-thread block (thread t owns i = t, t+256,
+ * ..., warp butterfly, then the 8 warp sums left to right); slice sums are
+ * added left to right.
+ */
+#ifndef ORACLE_SLICE
+#define ORACLE_SLICE 2048
+#endif
+static REAL FN(dot_sliced)(const REAL* x, const REAL* y, long n) {
+	REAL total = (REAL)0;
+	for (long s0 = 0; s0 < n; s0 += ORACLE_SLICE) {
+		long len = n - s0 < ORACLE_SLICE ? n - s0 : ORACLE_SLICE;
+		REAL th[256];
+		for (int t = 0; t < 256; ++t) {
+			REAL a = (REAL)0;
+			for (long i = t; i < len; i += 256) a = FMA(x[s0 + i], y[s0 + i], a);
+			th[t] = a;
+		}
+		REAL blk = (REAL)0;
+		for (int w = 0; w < 8; ++w) {
+			REAL s[32];
+			for (int l = 0; l < 32; ++l) s[l] = th[w * 32 + l];
+			for (int off = 16; off >= 1; off >>= 1) {
+				REAL t2[32];
+				for (int l = 0; l < 32; ++l) t2[l] = s[l] + s[l ^ off];
+				for (int l = 0; l < 32; ++l) s[l] = t2[l];
+			}
+			blk = blk + s[0];
+		}
+		total = total + blk;
+	}
+	return total;
+}
+
+/* ---- the solver ------------------------------------------------------ */
+
+int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n,
+		REAL eps, long max_iter, int order,
+		REAL* x_b_out, int* b_ixs_out, REAL* y_out, REAL* Binv_out,
+		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
+		long trace_cap, oracle_result* res) {
+	if (m <= 0 || n <= 0 || m > n) return -1;
+
+	const long chunk = 256; /* engine FTRAN chunk width (order = 1) */
+	REAL* Binv = (REAL*)calloc((size_t)m * m, sizeof(REAL));
+	REAL* c_b = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* x_b = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* y = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* e = (REAL*)malloc(sizeof(REAL) * n);
+	REAL* alpha = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* theta = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* row_q = (REAL*)malloc(sizeof(REAL) * m);
+	REAL* E_q = (REAL*)malloc(sizeof(REAL) * m);
+	int* b_ixs = (int*)malloc(sizeof(int) * m);
+	if (!Binv || !c_b || !x_b || !y || !e || !alpha || !theta || !row_q || !E_q || !b_ixs) return -2;
+
+	/* v4:272-277 */
+	for (long i = 0; i < m; ++i) {
+		Binv[i + i * m] = (REAL)1;
+		c_b[i] = c[n - m + i];
+		x_b[i] = b[i];
+		b_ixs[i] = (int)(n - m + i);
+		y[i] = c_b[i];
+	}
+
+	int status = 0; /* MaxIter */
+	long it = 0, pivots = 0;
+
+	do {
+		/* ---- pricing, v4:288-302 ---- */
+		#pragma omp parallel for schedule(static)
+		for (long j = 0; j < n; ++j) {
+			const REAL* col = A + j * m;
+			if (order == 0) {
+				e[j] = FN(dot_seq)(y, col, m, -c[j]);
+			} else {
+				/* engine: warp dot, then -c_j added last */
+				e[j] = FN(dot_warp)(y, col, m) - c[j];
+			}
+		}
+		long p = 0;
+		REAL min_val = e[0];
+		for (long j = 1; j < n; ++j)
+			if (e[j] < min_val) { min_val = e[j]; p = j; }
+		double gap_p = INFINITY;
+		for (long j = 0; j < n; ++j)
+			if (j != p && (double)e[j] - (double)min_val < gap_p) gap_p = (double)e[j] - (double)min_val;
+
+		if (min_val >= -eps) { status = 1; ++it; break; }
+
+		/* ---- FTRAN, v4:307-308 ---- */
+		const REAL* a_p = A + p * m;
+		if (order == 0) {
+			for (long i = 0; i < m; ++i) alpha[i] = (REAL)0;
+			#pragma omp parallel
+			{
+				#pragma omp for schedule(static)
+				for (long i0 = 0; i0 < m; i0 += 512) {
+					long i1 = i0 + 512 < m ? i0 + 512 : m;
+					for (long j = 0; j < m; ++j) {
+						const REAL aj = a_p[j];
+						const REAL* bc = Binv + j * m;
+						for (long i = i0; i < i1; ++i) alpha[i] = FMA(bc[i], aj, alpha[i]);
+					}
+				}
+			}
+		} else {
+			#pragma omp parallel for schedule(static)
+			for (long i0 = 0; i0 < m; i0 += 512) {
+				long i1 = i0 + 512 < m ? i0 + 512 : m;
+				REAL tot[512], part[512];
+				for (long i = i0; i < i1; ++i) tot[i - i0] = (REAL)0;
+				for (long j0 = 0; j0 < m; j0 += chunk) {
+					long j1 = j0 + chunk < m ? j0 + chunk : m;
+					for (long i = i0; i < i1; ++i) part[i - i0] = (REAL)0;
+					for (long j = j0; j < j1; ++j) {
+						const REAL aj = a_p[j];
+						const REAL* bc = Binv + j * m;
+						for (long i = i0; i < i1; ++i) part[i - i0] = FMA(bc[i], aj, part[i - i0]);
+					}
+					for (long i = i0; i < i1; ++i) tot[i - i0] = tot[i - i0] + part[i - i0];
+				}
+				for (long i = i0; i < i1; ++i) alpha[i] = tot[i - i0];
+			}
+		}
+
+		/* ---- ratio test, v4:199-208, 311-326 ---- */
+		long num_non_pos = 0;
+		for (long i = 0; i < m; ++i) {
+			int flag = alpha[i] > (REAL)0;
+			theta[i] = flag ? (x_b[i] / alpha[i]) : (REAL)INFINITY;
+			num_non_pos += !flag;
+		}
+		if (num_non_pos == m) { status = 2; ++it; break; }
+		long q = 0;
+		REAL min_theta = theta[0];
+		for (long i = 1; i < m; ++i)
+			if (theta[i] < min_theta) { min_theta = theta[i]; q = i; }
+		double gap_q = INFINITY;
+		for (long i = 0; i < m; ++i)
+			if (i != q && (double)theta[i] - (double)min_theta < gap_q) gap_q = (double)theta[i] - (double)min_theta;
+
+		if (pivots < trace_cap) {
+			if (trace_p) trace_p[pivots] = (int)p;
+			if (trace_q) trace_q[pivots] = (int)q;
+			if (trace_gap_p) trace_gap_p[pivots] = gap_p;
+			if (trace_gap_q) trace_gap_q[pivots] = gap_q;
+		}
+
+		/* ---- row extract + E_q + rank-1 update, v4:331-333 ---- */
+		const REAL alpha_q = alpha[q];
+		for (long j = 0; j < m; ++j) row_q[j] = Binv[q + j * m];
+		for (long i = 0; i < m; ++i)
+			E_q[i] = (i != q) ? (-alpha[i] / alpha_q) : (REAL)(1.0 / (double)alpha_q - 1.0);
+		#pragma omp parallel for schedule(static)
+		for (long j = 0; j < m; ++j) {
+			const REAL r = row_q[j];
+			REAL* bc = Binv + j * m;
+			for (long i = 0; i < m; ++i) bc[i] = FMA(E_q[i], r, bc[i]);
+		}
+
+		/* ---- bookkeeping, v4:339-342 ---- */
+		const REAL c_b_q = c_b[q];
+		c_b[q] = c[p];
+		b_ixs[q] = (int)p;
+
+		/* ---- x_b, v4:347-348 ---- */
+		REAL s = order == 0 ? FN(dot_seq)(row_q, b, m, (REAL)0) : FN(dot_sliced)(row_q, b, m);
+		for (long i = 0; i < m; ++i) x_b[i] = FMA(s, E_q[i], x_b[i]);
+
+		/* ---- y, v4:353-356 ---- */
+		s = order == 0 ? FN(dot_seq)(c_b, E_q, m, (REAL)0) : FN(dot_sliced)(c_b, E_q, m);
+		s += c[p] - c_b_q;
+		for (long i = 0; i < m; ++i) y[i] = FMA(s, row_q[i], y[i]);
+
+		++pivots;
+	} while (++it < max_iter);
+
+	/* v4:362-368 (computed for every status so callers can inspect MaxIter states) */
+	REAL z = order == 0 ? FN(dot_seq)(c_b, x_b, m, (REAL)0) : FN(dot_sliced)(c_b, x_b, m);
+
+	if (res) {
+		res->status = status;
+		res->iterations = it;
+		res->pivots = pivots;
+		res->z = (double)z;
+	}
+	if (x_b_out) memcpy(x_b_out, x_b, sizeof(REAL) * m);
+	if (b_ixs_out) memcpy(b_ixs_out, b_ixs, sizeof(int) * m);
+	if (y_out) memcpy(y_out, y, sizeof(REAL) * m);
+	if (Binv_out) memcpy(Binv_out, Binv, sizeof(REAL) * (size_t)m * m);
+
+	free(Binv); free(c_b); free(x_b); free(y); free(e); free(alpha);
+	free(theta); free(row_q); free(E_q); free(b_ixs);
+	return 0;
+}
+
+#undef FN
+#undef CAT
+#undef CAT_
