@@ -1,0 +1,150 @@
+/*
+ * b200lp — C ABI of the B200-native dense revised-simplex engine.
+ *
+ * Drop-in boundary for the reference's solver entry point
+ *     std::pair<real, SolveStatus> solve(real* A, real* b, real* c, real* x_b,
+ *                                        int* b_ixs, int m, int n, TimeStruct& t)
+ * (reference: src/v4_cub_reduction.cu:219, called once from main at :423).
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions shared with the reference:
+ *   - A is column-major m x n (v4:59-60), n counts ALL columns, the slack
+ *     (identity) block is the LAST m columns (v4:272-277); requires m <= n
+ *     (v4:402).
+ *   - standard form  max c'x  s.t.  Ax <= b, x >= 0, slack starting basis.
+ *   - entering column: most negative reduced cost over all n columns, lowest
+ *     index on ties (v4:288-302); optimal iff min >= -eps (v4:299).
+ *   - leaving row: min x_b/alpha over alpha > 0 (strict), lowest index on
+ *     ties; unbounded iff no row is eligible (v4:199-208, 319-325).
+ *   - x_b / b_ixs are returned in basis order, slack variables included
+ *     (v4:366-367, printed at v4:429-430).
+ *
+ * Every function returns B200LP_OK (0) or a negative error code; nothing in
+ * the library calls exit() (the reference does, v4:67-92).  Solver outcomes
+ * are statuses, not errors (v4:426-445).
+ */
+#ifndef B200LP_H
+#define B200LP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- solver outcome: mirrors `enum class SolveStatus` (v4:49-54) ---- */
+#define B200LP_STATUS_MAX_ITER       0
+#define B200LP_STATUS_OPTIMUM        1
+#define B200LP_STATUS_UNBOUNDED      2
+#define B200LP_STATUS_THETA_OVERFLOW 3 /* unreachable, kept for enum parity (v1 only) */
+
+/* ---- error codes ---- */
+#define B200LP_OK            0
+#define B200LP_ERR_ARG      -1 /* bad sizes / NULL pointers / m > n (v4:402) */
+#define B200LP_ERR_CUDA     -2 /* CUDA runtime failure, see b200lp_last_error() */
+#define B200LP_ERR_NO_GPU   -3 /* no sm_100 device: there is no CPU fallback */
+#define B200LP_ERR_STATE    -4 /* call order (e.g. run before upload) */
+
+/* ---- scalar type of an engine (`using real = float`, v4:12) ---- */
+#define B200LP_F32 0
+#define B200LP_F64 1
+
+typedef struct b200lp_engine b200lp_engine; /* opaque */
+
+typedef struct {
+	double  eps;          /* optimality tolerance, reference EPS = 1e-4 (v4:18) */
+	int64_t max_iter;     /* iteration cap, reference MAX_ITER = 5 (v4:19) */
+	int32_t device;       /* CUDA device ordinal */
+	int32_t grid_ctas;    /* persistent grid size; 0 = auto (multiple of the SM count) */
+	int32_t tile_shape;   /* update+FTRAN tile: 0 = auto, else warps along columns 1|2|4|8 */
+	int32_t check_slack;  /* 1: verify that the last m columns are the identity (default);
+	                         0: trust the caller like the reference does (v4:272) */
+	int32_t mode;         /* 0 = persistent cooperative kernel, 1 = one launch per phase */
+	int32_t reserved;
+} b200lp_options;
+
+typedef struct {
+	int32_t status;       /* B200LP_STATUS_* */
+	int32_t reserved;
+	int64_t iterations;   /* number of "# Iteration k" lines the reference prints (v4:287) */
+	int64_t pivots;
+	double  z;            /* c_b . x_b (v4:365) */
+	double  min_reduced_cost; /* last pricing minimum */
+	double  ms_upload;    /* host->device, CUDA events */
+	double  ms_solve;     /* pivot loop on the device, CUDA events */
+	double  ms_download;  /* device->host */
+	int64_t kernel_launches;
+} b200lp_result;
+
+/* defaults: eps 1e-4, max_iter 5 (the reference's constants), device 0, auto grid */
+void b200lp_default_options(b200lp_options* opt);
+
+/*
+ * One-call replacement of the reference's solve() (v4:219): host buffers in,
+ * host buffers out; allocates and frees all device state per call like the
+ * reference (v4:245-264, 370-377).  x_b (m) and b_ixs (m) are written for
+ * every status (the reference only fills them on OptimumFound, v4:363-368).
+ * trace_pq (optional) receives (p, q) per pivot, 2*trace_cap ints.
+ */
+int b200lp_solve_f64(const double* A, const double* b, const double* c, int64_t m, int64_t n,
+		const b200lp_options* opt, double* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
+int b200lp_solve_f32(const float* A, const float* b, const float* c, int64_t m, int64_t n,
+		const b200lp_options* opt, float* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
+
+/* ---- handle API: device state survives between calls (bench, windows, tests) ---- */
+
+/* allocates A_N, B^-1 and all vectors for an m x n problem (v4:245-264) */
+int b200lp_create(int32_t dtype, int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out);
+int b200lp_destroy(b200lp_engine* e);
+
+/* H2D of A (col-major m x n), b (m), c (n) (v4:269-271) followed by the slack-basis
+ * initial state (v4:272-279).  Pointers are host memory of the engine's dtype. */
+int b200lp_upload(b200lp_engine* e, const void* A, const void* b, const void* c);
+
+/* synthetic dense LP generated on the device (bench; same numbers as oracle/lpgen_dense_*) */
+int b200lp_generate_dense(b200lp_engine* e, uint64_t seed);
+
+/* back to the slack basis: B^-1 = I, x_b = b, y = c_b = c[n-m..n) (v4:272-277) */
+int b200lp_reset(b200lp_engine* e);
+
+/* run at most `iterations` more iterations of the loop at v4:286-359 (blocking) */
+int b200lp_run(b200lp_engine* e, int64_t iterations, b200lp_result* res);
+/* same, without waiting: returns after the launch; pair with b200lp_wait() */
+int b200lp_run_async(b200lp_engine* e, int64_t iterations);
+int b200lp_wait(b200lp_engine* e, b200lp_result* res);
+
+/* D2H of the basis-ordered solution (v4:366-367); any pointer may be NULL */
+int b200lp_download(b200lp_engine* e, void* x_b, int32_t* b_ixs, void* y);
+/* D2H of B^-1 (col-major m x m) after flushing a pending rank-1 update (tests) */
+int b200lp_download_binv(b200lp_engine* e, void* Binv);
+/* (p, q) of the first min(pivots, cap) pivots */
+int b200lp_download_trace(b200lp_engine* e, int32_t* trace_pq, int64_t cap, int64_t* n_out);
+
+/* ---- per-phase entry points (unit tests, sharded multi-GPU driver) ----
+ * Each runs ONE phase of the pivot as its own launch on the engine's stream and
+ * waits for it.  Order within a pivot: price -> update_ftran -> ratio -> pivot_update. */
+/* pricing fused with argmin (replaces cublasSgemm + cub ArgMin, v4:289-296) */
+int b200lp_phase_price(b200lp_engine* e, int64_t* p, double* min_e);
+/* pending rank-1 update of B^-1 fused with alpha = B^-1 A[:,p] (v4:307-308 + v4:333 of the previous pivot) */
+int b200lp_phase_update_ftran(b200lp_engine* e, int64_t p);
+/* fused masked-argmin ratio test (v4:311-325); eligible = number of rows with alpha > 0 */
+int b200lp_phase_ratio(b200lp_engine* e, int64_t* q, int64_t* eligible);
+/* row extract, E_q, c_b/b_ixs bookkeeping, x_b and y updates (v4:331-332, 339-356) */
+int b200lp_phase_pivot_update(b200lp_engine* e, int64_t p, int64_t q);
+/* device vectors for inspection: which = 0 alpha, 1 E_q, 2 row_q, 3 x_b, 4 y, 5 c_b (length m) */
+int b200lp_download_vector(b200lp_engine* e, int32_t which, void* out);
+
+/* ---- introspection ---- */
+void*       b200lp_stream(b200lp_engine* e);     /* cudaStream_t the engine launches on */
+int         b200lp_grid_ctas(b200lp_engine* e);
+int         b200lp_dense_columns(b200lp_engine* e); /* n - m when the slack block was recognised */
+int64_t     b200lp_bytes_per_pivot(b200lp_engine* e); /* algorithmic bytes: s*(2 m^2 + m (n-m)) */
+const char* b200lp_last_error(void);
+const char* b200lp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LP_H */

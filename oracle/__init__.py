@@ -151,3 +151,82 @@ def u01(seed: int, stream: int, idx: int) -> float:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+# ---------------------------------------------------------------- the reference's own v4 build (GPU only)
+
+_REF_DIR = os.path.join(_HERE, "_ref")
+_ref_libs: dict = {}
+
+
+def build_ref() -> bool:
+    """Run make_ref.sh when /root/reference is mounted (build container); no-op on the GPU box."""
+    src = "/root/reference/src/v4_cub_reduction.cu"
+    if not os.path.exists(src):
+        return ref_available()
+    outs = [os.path.join(_REF_DIR, f) for f in ("libv4ref_f64.so", "libv4ref_f32.so", "v4_stock.out")]
+    deps = [src, os.path.join(_HERE, "make_ref.sh"), os.path.join(_HERE, "ref_harness.cu")]
+    if all(os.path.exists(o) for o in outs) and min(map(os.path.getmtime, outs)) > max(map(os.path.getmtime, deps)):
+        return True
+    subprocess.run([os.path.join(_HERE, "make_ref.sh")], check=True, capture_output=True)
+    return ref_available()
+
+
+def ref_available(dtype=np.float64) -> bool:
+    name = "libv4ref_f64.so" if np.dtype(dtype) == np.float64 else "libv4ref_f32.so"
+    return os.path.exists(os.path.join(_REF_DIR, name))
+
+
+def ref_stock_binary() -> str | None:
+    p = os.path.join(_REF_DIR, "v4_stock.out")
+    return p if os.path.exists(p) else None
+
+
+def _ref_lib(dtype):
+    dt = np.dtype(dtype)
+    if dt not in _ref_libs:
+        name = "libv4ref_f64.so" if dt == np.float64 else "libv4ref_f32.so"
+        L = C.CDLL(os.path.join(_REF_DIR, name))
+        L.ref_solve.restype = C.c_int
+        L.ref_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
+                                C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_sizeof_real.restype = C.c_int
+        assert L.ref_sizeof_real() == dt.itemsize
+        _ref_libs[dt] = L
+    return _ref_libs[dt]
+
+
+@dataclass
+class RefSolution:
+    status: int
+    iterations: int
+    pivots: int
+    z: float
+    x_b: np.ndarray
+    b_ixs: np.ndarray
+    trace_p: np.ndarray
+    trace_q: np.ndarray
+    secs_total: float
+    secs_loop: float
+
+
+def ref_solve(A, b, c, eps=1e-4, max_iter=5, trace_cap=None) -> RefSolution:
+    """The reference's own solve() (v4:219, patched per make_ref.sh) on the current CUDA device."""
+    dt = np.dtype(A.dtype)
+    A = np.asfortranarray(A, dtype=dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    c = np.ascontiguousarray(c, dtype=dt)
+    m, n = A.shape
+    cap = int(trace_cap if trace_cap is not None else min(max_iter, 1 << 22))
+    x_b = np.zeros(m, dt)
+    b_ixs = np.zeros(m, np.int32)
+    tr = np.full((max(cap, 1), 2), -1, np.int32)
+    z, it, st, sl = C.c_double(0), C.c_long(0), C.c_double(0), C.c_double(0)
+    status = _ref_lib(dt).ref_solve(_ptr(A), _ptr(b), _ptr(c), m, n, eps, int(max_iter), _ptr(x_b), _ptr(b_ixs),
+                                    _ptr(tr), cap, C.byref(z), C.byref(it), C.byref(st), C.byref(sl))
+    if status < 0:
+        raise RuntimeError("reference solve failed (CUDA error)")
+    piv = it.value - 1 if status in (OPTIMUM, UNBOUNDED) else it.value
+    k = min(piv, cap)
+    return RefSolution(status, it.value, piv, z.value, x_b, b_ixs, tr[:k, 0].copy(), tr[:k, 1].copy(), st.value, sl.value)

@@ -49,44 +49,47 @@ static REAL FN(dot_seq)(const REAL* x, const REAL* y, long n, REAL init) {
 }
 
 /*
- * Engine order for a length-n dot product done by one warp: lane l owns
- * elements {k*32*V + l*V + v}, accumulates each v-slot in its own chain
- * (V = 16 bytes / sizeof(REAL)), sums the slots left to right, then a
- * butterfly (xor 16,8,4,2,1) over the 32 lanes.
+ * Engine order of the pricing dot product (price_phase in kernels.cuh): one
+ * 256-thread CTA per column, thread t owns the 16-byte vectors t, t+256, ...
+ * (V = 16/sizeof(REAL) elements each), one fma chain per vector slot, slots
+ * summed left to right, butterfly (xor 16,8,4,2,1) inside each warp, then the
+ * 8 warp sums left to right.
  */
-static REAL FN(dot_warp)(const REAL* x, const REAL* y, long n) {
+static REAL FN(dot_block256)(const REAL* x, const REAL* y, long n) {
 	enum { V = 16 / sizeof(REAL) };
-	REAL lane[32][V];
-	for (int l = 0; l < 32; ++l)
-		for (int v = 0; v < V; ++v) lane[l][v] = (REAL)0;
-	for (long base = 0; base < n; base += 32 * V)
-		for (int l = 0; l < 32; ++l)
-			for (int v = 0; v < V; ++v) {
-				long i = base + (long)l * V + v;
-				if (i < n) lane[l][v] = FMA(x[i], y[i], lane[l][v]);
-			}
-	REAL s[32];
-	for (int l = 0; l < 32; ++l) {
-		REAL a = lane[l][0];
-		for (int v = 1; v < V; ++v) a = a + lane[l][v];
-		s[l] = a;
+	REAL th[256];
+	for (int t = 0; t < 256; ++t) {
+		REAL acc[V];
+		for (int v = 0; v < V; ++v) acc[v] = (REAL)0;
+		for (long base = (long)t * V; base < n; base += 256 * V)
+			for (int v = 0; v < V; ++v)
+				if (base + v < n) acc[v] = FMA(x[base + v], y[base + v], acc[v]);
+		REAL a = acc[0];
+		for (int v = 1; v < V; ++v) a = a + acc[v];
+		th[t] = a;
 	}
-	for (int off = 16; off >= 1; off >>= 1) {
-		REAL t[32];
-		for (int l = 0; l < 32; ++l) t[l] = s[l] + s[l ^ off];
-		for (int l = 0; l < 32; ++l) s[l] = t[l];
+	REAL tot = (REAL)0;
+	for (int w = 0; w < 8; ++w) {
+		REAL s[32];
+		for (int l = 0; l < 32; ++l) s[l] = th[w * 32 + l];
+		for (int off = 16; off >= 1; off >>= 1) {
+			REAL t2[32];
+			for (int l = 0; l < 32; ++l) t2[l] = s[l] + s[l ^ off];
+			for (int l = 0; l < 32; ++l) s[l] = t2[l];
+		}
+		tot = w == 0 ? s[0] : tot + s[0];
 	}
-	return s[0];
+	return tot;
 }
 
 /*
  * Engine order for the O(m) bookkeeping dots: fixed slices of ORACLE_SLICE
- * elements, each reduced by one 256-thread block (thread t owns i = t, t+256,
- * ..., warp butterfly, then the 8 warp sums left to right); slice sums are
- * added left to right.
+ * elements, each reduced by one 256-thread block (thread t owns element t, warp
+ * butterfly, then the 8 warp sums left to right); slice sums are added left to
+ * right (book1_phase / book2_phase / objective in kernels.cuh).
  */
 #ifndef ORACLE_SLICE
-#define ORACLE_SLICE 2048
+#define ORACLE_SLICE 256
 #endif
 static REAL FN(dot_sliced)(const REAL* x, const REAL* y, long n) {
 	REAL total = (REAL)0;
@@ -145,6 +148,16 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 		y[i] = c_b[i];
 	}
 
+	/* order = 1: like the engine, recognise an identity slack block (v4:272 assumes it) */
+	long ns = n;
+	if (order == 1) {
+		int ident = 1;
+		for (long j = 0; j < m && ident; ++j)
+			for (long i = 0; i < m; ++i)
+				if (A[i + (n - m + j) * m] != (REAL)(i == j)) { ident = 0; break; }
+		if (ident) ns = n - m;
+	}
+
 	int status = 0; /* MaxIter */
 	long it = 0, pivots = 0;
 
@@ -155,9 +168,12 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 			const REAL* col = A + j * m;
 			if (order == 0) {
 				e[j] = FN(dot_seq)(y, col, m, -c[j]);
+			} else if (j < ns) {
+				/* engine: block dot, then "- c_j" */
+				e[j] = FN(dot_block256)(col, y, m) - c[j];
 			} else {
-				/* engine: warp dot, then -c_j added last */
-				e[j] = FN(dot_warp)(y, col, m) - c[j];
+				/* engine: recognised slack column, e_j = y_k - c_j (no matrix bytes) */
+				e[j] = y[j - ns] - c[j];
 			}
 		}
 		long p = 0;
@@ -187,20 +203,28 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 				}
 			}
 		} else {
+			/* engine (update_ftran_phase): 32-column sub-blocks, one fma chain each;
+			 * pairwise tree over the 8 sub-blocks of a 256-column chunk; chunks left to right */
 			#pragma omp parallel for schedule(static)
-			for (long i0 = 0; i0 < m; i0 += 512) {
-				long i1 = i0 + 512 < m ? i0 + 512 : m;
-				REAL tot[512], part[512];
-				for (long i = i0; i < i1; ++i) tot[i - i0] = (REAL)0;
+			for (long i0 = 0; i0 < m; i0 += 256) {
+				long i1 = i0 + 256 < m ? i0 + 256 : m;
+				REAL tot[256], sub[8][256];
 				for (long j0 = 0; j0 < m; j0 += chunk) {
-					long j1 = j0 + chunk < m ? j0 + chunk : m;
-					for (long i = i0; i < i1; ++i) part[i - i0] = (REAL)0;
-					for (long j = j0; j < j1; ++j) {
-						const REAL aj = a_p[j];
-						const REAL* bc = Binv + j * m;
-						for (long i = i0; i < i1; ++i) part[i - i0] = FMA(bc[i], aj, part[i - i0]);
+					for (int sb = 0; sb < 8; ++sb) {
+						for (long i = i0; i < i1; ++i) sub[sb][i - i0] = (REAL)0;
+						long ja = j0 + sb * 32, jb = ja + 32 < m ? ja + 32 : m;
+						for (long j = ja; j < jb; ++j) {
+							const REAL aj = a_p[j];
+							const REAL* bc = Binv + j * m;
+							for (long i = i0; i < i1; ++i) sub[sb][i - i0] = FMA(bc[i], aj, sub[sb][i - i0]);
+						}
 					}
-					for (long i = i0; i < i1; ++i) tot[i - i0] = tot[i - i0] + part[i - i0];
+					for (long i = i0; i < i1; ++i) {
+						const long r = i - i0;
+						const REAL c8 = ((sub[0][r] + sub[1][r]) + (sub[2][r] + sub[3][r]))
+						              + ((sub[4][r] + sub[5][r]) + (sub[6][r] + sub[7][r]));
+						tot[r] = j0 == 0 ? c8 : tot[r] + c8;
+					}
 				}
 				for (long i = i0; i < i1; ++i) alpha[i] = tot[i - i0];
 			}

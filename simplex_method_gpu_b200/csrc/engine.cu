@@ -1,0 +1,608 @@
+// Host side of the B200 dense revised-simplex engine and its C ABI
+// (include/b200lp.h).  Replaces the host half of the reference's solve()
+// (src/v4_cub_reduction.cu:219-380): allocation (v4:245-264), H2D + initial
+// state (v4:269-279), the loop driver (v4:286-359, here ONE cooperative
+// launch) and the read-back (v4:362-368).  No cuBLAS, no CUB, no CPU fallback.
+#include "../../include/b200lp.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace b200lp;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+	g_err = msg;
+	return code;
+}
+
+#define CU(call)                                                                          \
+	do {                                                                                  \
+		cudaError_t e_ = (call);                                                          \
+		if (e_ != cudaSuccess)                                                            \
+			return fail(B200LP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+struct b200lp_engine {
+	virtual ~b200lp_engine() {}
+	virtual int upload(const void* A, const void* b, const void* c) = 0;
+	virtual int generate_dense(uint64_t seed) = 0;
+	virtual int reset() = 0;
+	virtual int run_async(int64_t iters) = 0;
+	virtual int wait(b200lp_result* res) = 0;
+	virtual int download(void* x_b, int32_t* b_ixs, void* y) = 0;
+	virtual int download_binv(void* Binv) = 0;
+	virtual int download_trace(int32_t* pq, int64_t cap, int64_t* n_out) = 0;
+	virtual int phase_price(int64_t* p, double* min_e) = 0;
+	virtual int phase_update_ftran(int64_t p) = 0;
+	virtual int phase_ratio(int64_t* q, int64_t* eligible) = 0;
+	virtual int phase_pivot_update(int64_t p, int64_t q) = 0;
+	virtual int download_vector(int32_t which, void* out) = 0;
+	virtual int64_t bytes_per_pivot() const = 0;
+	cudaStream_t stream = nullptr;
+	int grid = 0;
+	long long ns = 0;
+	double ms_upload = 0;
+};
+
+namespace {
+
+template <typename T>
+class Engine final : public b200lp_engine {
+public:
+	Engine(int64_t m, int64_t n, const b200lp_options& o) : opt(o) {
+		std::memset(&d, 0, sizeof(d));
+		std::memset(&hc, 0, sizeof(hc));
+		d.m = m;
+		d.n = n;
+		constexpr long long rowq = 32 * VecT<T>::N;
+		d.ld = (m + rowq - 1) / rowq * rowq;
+		d.nchunk = (int)((m + CHUNK - 1) / CHUNK);
+		d.nslice = (int)((m + SLICE - 1) / SLICE);
+		d.eps = sizeof(T) == 4 ? (double)(float)o.eps : o.eps;
+		d.trace_cap = std::max<int64_t>(1, std::min<int64_t>(o.max_iter, (int64_t)1 << 22));
+	}
+
+	~Engine() override { release(); }
+
+	int init() {
+		CU(cudaSetDevice(opt.device));
+		cudaDeviceProp prop;
+		CU(cudaGetDeviceProperties(&prop, opt.device));
+		if (prop.major < 10)
+			return fail(B200LP_ERR_NO_GPU, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+				", the engine is built for sm_100a only");
+		num_sms = prop.multiProcessorCount;
+		CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		CU(cudaEventCreate(&ev0));
+		CU(cudaEventCreate(&ev1));
+		CU(cudaEventCreate(&ev2));
+
+		const size_t ld = (size_t)d.ld, m = (size_t)d.m;
+		CU(alloc(&d.B, ld * m));
+		T* vecs[8];
+		for (auto& v : vecs) CU(alloc(&v, ld));
+		d.b = vecs[0]; hb = vecs[0];
+		d.y = vecs[1]; d.x_b = vecs[2]; d.c_b = vecs[3]; d.alpha = vecs[4]; d.E_q = vecs[5]; d.row_q = vecs[6];
+		spare = vecs[7];
+		CU(alloc(&hcst, (size_t)d.n));
+		d.c = hcst;
+		CU(alloc(&d.alpha_part, (size_t)d.nchunk * ld));
+		CU(alloc(&d.dpart, (size_t)2 * d.nslice));
+		CU(alloc(&d.b_ixs, m));
+		CU(alloc(&d.ctl, 1));
+		CU(alloc(&d.trace, (size_t)d.trace_cap));
+		CU(cudaMemsetAsync(d.ctl, 0, sizeof(Ctl), stream));
+		CU(cudaMallocHost(&pinned, sizeof(Ctl) + 64));
+
+		// persistent grid: co-resident CTAs only (cooperative launch)
+		int occ = 0;
+		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, 0));
+		if (occ < 1) return fail(B200LP_ERR_CUDA, "persistent kernel does not fit on an SM");
+		max_grid = occ * num_sms;
+		const double work = (double)d.ld * (double)d.n;
+		int g;
+		if (opt.grid_ctas > 0) g = opt.grid_ctas;
+		else if (work <= 64.0 * 1024) g = 1;                       // tiny LPs: barriers are pure latency
+		else if (work <= 4.0 * 1024 * 1024) g = num_sms;
+		else g = num_sms * std::min(occ, 4);
+		grid = std::max(1, std::min(g, max_grid));
+		CU(alloc(&d.cand, (size_t)max_grid + 2));
+		CU(alloc(&d.cnt, (size_t)max_grid + 2));
+
+		// tile shape of the update+FTRAN pass: widest row tile that still gives every CTA a tile
+		wc = 8;
+		for (int cand_wc : {1, 2, 4, 8}) {
+			const long long tr = (long long)(NWARP / cand_wc) * 32 * VecT<T>::N;
+			const long long tiles = (d.ld + tr - 1) / tr * d.nchunk;
+			if (tiles >= grid) { wc = cand_wc; break; }
+		}
+		if (opt.tile_shape == 1 || opt.tile_shape == 2 || opt.tile_shape == 4 || opt.tile_shape == 8) wc = opt.tile_shape;
+		return B200LP_OK;
+	}
+
+	// ---- data in -------------------------------------------------------
+
+	int upload(const void* Av, const void* bv, const void* cv) override {
+		const T* A = static_cast<const T*>(Av);
+		const T* b = static_cast<const T*>(bv);
+		const T* c = static_cast<const T*>(cv);
+		const long long m = d.m, n = d.n, ld = d.ld;
+		CU(cudaSetDevice(opt.device));
+
+		// Is the last m x m block the identity the reference assumes (v4:272)?  If so
+		// those columns are priced and FTRAN'd as unit vectors and never stored.
+		bool slack_ok = true;
+		if (opt.check_slack) slack_ok = host_is_identity(A + (size_t)(n - m) * m, m);
+		const long long ns_new = slack_ok ? n - m : n;
+		if (!hA || ns_new != d.ns) {
+			if (hA) cudaFree(hA);
+			hA = nullptr;
+			if (ns_new > 0) CU(alloc(&hA, (size_t)ld * ns_new));
+			d.A = hA;
+			d.ns = ns_new;
+			ns = ns_new;
+		}
+		CU(cudaEventRecord(ev0, stream));
+		if (d.ns > 0)
+			CU(cudaMemcpy2DAsync(hA, ld * sizeof(T), A, m * sizeof(T), m * sizeof(T), (size_t)d.ns, cudaMemcpyHostToDevice, stream));
+		CU(cudaMemsetAsync(hb, 0, ld * sizeof(T), stream));
+		CU(cudaMemcpyAsync(hb, b, m * sizeof(T), cudaMemcpyHostToDevice, stream));
+		CU(cudaMemcpyAsync(hcst, c, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+		if (ld > m && d.ns > 0) {
+			k_zero_pad<T><<<num_sms * 4, 256, 0, stream>>>(hA, m, ld, d.ns);
+			launches++;
+		}
+		CU(cudaEventRecord(ev1, stream));
+		have_data = true;
+		int rc = reset();
+		if (rc) return rc;
+		CU(cudaStreamSynchronize(stream));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, ev0, ev1));
+		ms_upload = ms;
+		return B200LP_OK;
+	}
+
+	int generate_dense(uint64_t seed) override {
+		CU(cudaSetDevice(opt.device));
+		const long long ns_new = d.n - d.m;
+		if (!hA || ns_new != d.ns) {
+			if (hA) cudaFree(hA);
+			hA = nullptr;
+			if (ns_new > 0) CU(alloc(&hA, (size_t)d.ld * ns_new));
+			d.A = hA;
+			d.ns = ns_new;
+			ns = ns_new;
+		}
+		k_generate_dense<T><<<num_sms * 8, 256, 0, stream>>>(hA, hb, hcst, d.m, d.n, d.ns, d.ld, seed);
+		launches++;
+		CU(cudaGetLastError());
+		have_data = true;
+		return reset();
+	}
+
+	int reset() override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "reset before upload/generate");
+		CU(cudaSetDevice(opt.device));
+		k_reset<T><<<num_sms * 8, 256, 0, stream>>>(d);
+		launches++;
+		CU(cudaGetLastError());
+		std::memset(&hc, 0, sizeof(hc));
+		CU(cudaMemsetAsync(d.ctl, 0, sizeof(Ctl), stream));
+		CU(cudaStreamSynchronize(stream));
+		return B200LP_OK;
+	}
+
+	// ---- the loop ------------------------------------------------------
+
+	int run_async(int64_t iters) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "run before upload/generate");
+		CU(cudaSetDevice(opt.device));
+		in_flight = true;
+		if (hc.done || iters <= 0) {
+			CU(cudaEventRecord(ev0, stream));
+			CU(cudaEventRecord(ev1, stream));
+			return B200LP_OK;
+		}
+		if (opt.mode == 1) return run_phases(iters);
+		hc.it_end = hc.iter + iters;
+		CU(push_ctl());
+		CU(cudaEventRecord(ev0, stream));
+		void* args[] = {&d};
+		const void* fn = wc == 1 ? (const void*)simplex_persistent<T, 1>
+		               : wc == 2 ? (const void*)simplex_persistent<T, 2>
+		               : wc == 4 ? (const void*)simplex_persistent<T, 4>
+		                         : (const void*)simplex_persistent<T, 8>;
+		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, 0, stream));
+		launches++;
+		CU(cudaEventRecord(ev1, stream));
+		return B200LP_OK;
+	}
+
+	int wait(b200lp_result* res) override {
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		CU(cudaGetLastError());
+		float ms = 0;
+		if (in_flight) {
+			CU(cudaEventElapsedTime(&ms, ev0, ev1));
+			CU(pull_ctl());
+		}
+		in_flight = false;
+		if (res) {
+			std::memset(res, 0, sizeof(*res));
+			res->status = hc.status;
+			res->iterations = hc.iter;
+			res->pivots = hc.pivots;
+			res->z = hc.z;
+			res->min_reduced_cost = hc.min_e;
+			res->ms_solve = ms;
+			res->ms_upload = ms_upload;
+			res->kernel_launches = launches;
+		}
+		return B200LP_OK;
+	}
+
+	// ---- data out ------------------------------------------------------
+
+	int download(void* x_b, int32_t* b_ixs, void* y) override {
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		if (x_b) CU(cudaMemcpy(x_b, d.x_b, d.m * sizeof(T), cudaMemcpyDeviceToHost));
+		if (b_ixs) CU(cudaMemcpy(b_ixs, d.b_ixs, d.m * sizeof(int), cudaMemcpyDeviceToHost));
+		if (y) CU(cudaMemcpy(y, d.y, d.m * sizeof(T), cudaMemcpyDeviceToHost));
+		return B200LP_OK;
+	}
+
+	int download_binv(void* Binv) override {
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		if (hc.pending) {
+			launch_update_ftran(true, false, 0);
+			CU(cudaGetLastError());
+			hc.pending = 0;
+			CU(push_ctl());
+		}
+		CU(cudaStreamSynchronize(stream));
+		CU(cudaMemcpy2D(Binv, d.m * sizeof(T), d.B, d.ld * sizeof(T), d.m * sizeof(T), (size_t)d.m, cudaMemcpyDeviceToHost));
+		return B200LP_OK;
+	}
+
+	int download_trace(int32_t* pq, int64_t cap, int64_t* n_out) override {
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		const int64_t k = std::max<int64_t>(0, std::min<int64_t>({cap, (int64_t)hc.pivots, (int64_t)d.trace_cap}));
+		if (k > 0 && pq) CU(cudaMemcpy(pq, d.trace, (size_t)k * sizeof(int2), cudaMemcpyDeviceToHost));
+		if (n_out) *n_out = k;
+		return B200LP_OK;
+	}
+
+	int download_vector(int32_t which, void* out) override {
+		const T* src = which == 0 ? d.alpha : which == 1 ? d.E_q : which == 2 ? d.row_q
+		             : which == 3 ? d.x_b : which == 4 ? d.y : which == 5 ? d.c_b : nullptr;
+		if (!src || !out) return fail(B200LP_ERR_ARG, "download_vector: bad selector");
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		CU(cudaMemcpy(out, src, d.m * sizeof(T), cudaMemcpyDeviceToHost));
+		return B200LP_OK;
+	}
+
+	// ---- one launch per phase (tests, mode 1) ---------------------------
+
+	int phase_price(int64_t* p, double* min_e) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		CU(cudaSetDevice(opt.device));
+		k_price<T><<<grid, NT, 0, stream>>>(d);
+		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 0);
+		launches += 2;
+		CU(cudaGetLastError());
+		CU(pull_ctl_fields());
+		if (p) *p = hc.p;
+		if (min_e) *min_e = hc.min_e;
+		return B200LP_OK;
+	}
+
+	int phase_update_ftran(int64_t p) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (p < 0 || p >= d.n) return fail(B200LP_ERR_ARG, "entering column out of range");
+		CU(cudaSetDevice(opt.device));
+		launch_update_ftran(hc.pending != 0, true, p);
+		CU(cudaGetLastError());
+		hc.pending = 0;
+		hc.p = p;
+		CU(cudaStreamSynchronize(stream));
+		return B200LP_OK;
+	}
+
+	int phase_ratio(int64_t* q, int64_t* eligible) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		CU(cudaSetDevice(opt.device));
+		k_ratio<T><<<grid, NT, 0, stream>>>(d);
+		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 1);
+		launches += 2;
+		CU(cudaGetLastError());
+		CU(pull_ctl_fields());
+		long long el = 0;
+		CU(cudaMemcpy(&el, d.cnt + grid, sizeof(long long), cudaMemcpyDeviceToHost));
+		if (q) *q = hc.q;
+		if (eligible) *eligible = el;
+		return B200LP_OK;
+	}
+
+	int phase_pivot_update(int64_t p, int64_t q) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (p < 0 || p >= d.n || q < 0 || q >= d.m) return fail(B200LP_ERR_ARG, "pivot out of range");
+		CU(cudaSetDevice(opt.device));
+		k_book1<T><<<grid, NT, 0, stream>>>(d, p, q);
+		k_book2<T><<<grid, NT, 0, stream>>>(d, p, q);
+		launches += 2;
+		CU(cudaGetLastError());
+		if (hc.pivots < d.trace_cap) {
+			const int2 pq = make_int2((int)p, (int)q);
+			CU(cudaMemcpyAsync(d.trace + hc.pivots, &pq, sizeof(int2), cudaMemcpyHostToDevice, stream));
+		}
+		CU(cudaStreamSynchronize(stream));
+		hc.pending = 1;
+		hc.pivots++;
+		hc.iter++;
+		hc.p = p;
+		hc.q = q;
+		return B200LP_OK;
+	}
+
+	int64_t bytes_per_pivot() const override {
+		return (int64_t)sizeof(T) * (2 * d.m * d.m + d.m * (d.n - d.m));
+	}
+
+private:
+	template <typename U>
+	cudaError_t alloc(U** p, size_t count) {
+		cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(U));
+		if (e == cudaSuccess) owned.push_back((void*)*p);
+		return e;
+	}
+
+	void release() {
+		if (stream) cudaStreamSynchronize(stream);
+		for (void* p : owned)
+			if (p != (void*)hA) cudaFree(p);
+		if (hA) cudaFree(hA);
+		owned.clear();
+		if (pinned) cudaFreeHost(pinned);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
+		if (ev2) cudaEventDestroy(ev2);
+		if (stream) cudaStreamDestroy(stream);
+	}
+
+	static bool host_is_identity(const T* S, long long m) {
+		const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		const unsigned nt = (unsigned)std::max<long long>(1, std::min<long long>(hw, m / 64));
+		std::atomic<bool> ok{true};
+		auto work = [&](long long j0, long long j1) {
+			for (long long j = j0; j < j1 && ok.load(std::memory_order_relaxed); ++j) {
+				const T* col = S + (size_t)j * m;
+				bool good = true;
+				for (long long i = 0; i < m; ++i) good &= (col[i] == (i == j ? T(1) : T(0)));
+				if (!good) ok.store(false, std::memory_order_relaxed);
+			}
+		};
+		if (nt == 1) { work(0, m); return ok; }
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, m * t / nt, m * (t + 1) / nt);
+		for (auto& t : th) t.join();
+		return ok;
+	}
+
+	cudaError_t push_ctl() {
+		Ctl* st = static_cast<Ctl*>(pinned);
+		*st = hc;
+		st->bar = 0;
+		cudaError_t e = cudaMemcpyAsync(d.ctl, st, sizeof(Ctl), cudaMemcpyHostToDevice, stream);
+		if (e != cudaSuccess) return e;
+		// the staging buffer is reused: make sure the copy has been consumed
+		return cudaStreamSynchronize(stream);
+	}
+
+	cudaError_t pull_ctl() {
+		return cudaMemcpy(&hc, d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
+	}
+
+	// phase mode: only p / q / min_e come from the device, counters live on the host
+	cudaError_t pull_ctl_fields() {
+		Ctl t;
+		cudaError_t e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess) return e;
+		e = cudaMemcpy(&t, d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) return e;
+		hc.p = t.p; hc.q = t.q; hc.min_e = t.min_e;
+		return cudaSuccess;
+	}
+
+	void launch_update_ftran(bool update, bool ftran, long long p) {
+		const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
+		const long long tiles = (d.ld + tr - 1) / tr * d.nchunk;
+		const int g = (int)std::max<long long>(1, std::min<long long>(tiles, grid));
+#define LAUNCH_UF(WC_)                                                                                    \
+		do {                                                                                              \
+			if (update && ftran) k_update_ftran<T, WC_, true, true><<<g, NT, 0, stream>>>(d, p);          \
+			else if (update)     k_update_ftran<T, WC_, true, false><<<g, NT, 0, stream>>>(d, p);         \
+			else                 k_update_ftran<T, WC_, false, true><<<g, NT, 0, stream>>>(d, p);         \
+		} while (0)
+		if (wc == 1) LAUNCH_UF(1); else if (wc == 2) LAUNCH_UF(2); else if (wc == 4) LAUNCH_UF(4); else LAUNCH_UF(8);
+#undef LAUNCH_UF
+		launches++;
+	}
+
+	// mode 1: the loop of v4:286-359 driven from the host, one launch per phase and
+	// one blocking read-back per decision (what the reference does, minus the libraries)
+	int run_phases(int64_t iters) {
+		CU(cudaEventRecord(ev0, stream));
+		const long long it_end = hc.iter + iters;
+		hc.status = B200LP_STATUS_MAX_ITER;
+		while (hc.iter < it_end) {
+			int64_t p = 0, q = 0, el = 0;
+			double mn = 0;
+			int rc = phase_price(&p, &mn);
+			if (rc) return rc;
+			if (mn >= -d.eps) { hc.status = B200LP_STATUS_OPTIMUM; hc.done = 1; hc.iter++; break; }
+			if ((rc = phase_update_ftran(p))) return rc;
+			if ((rc = phase_ratio(&q, &el))) return rc;
+			if (el == 0) { hc.status = B200LP_STATUS_UNBOUNDED; hc.done = 1; hc.iter++; break; }
+			if ((rc = phase_pivot_update(p, q))) return rc;
+		}
+		k_objective<T><<<1, NT, 0, stream>>>(d);
+		launches++;
+		CU(cudaEventRecord(ev1, stream));
+		CU(cudaStreamSynchronize(stream));
+		Ctl t;
+		CU(cudaMemcpy(&t, d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+		hc.z = t.z;
+		CU(push_ctl());
+		return B200LP_OK;
+	}
+
+	b200lp_options opt;
+	Dev<T> d;
+	Ctl hc;                    // host mirror of the control block
+	T* hA = nullptr;           // mutable aliases of the const members of d
+	T* hb = nullptr;
+	T* hcst = nullptr;
+	T* spare = nullptr;
+	void* pinned = nullptr;
+	std::vector<void*> owned;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	int num_sms = 0, max_grid = 0, wc = 1;
+	bool have_data = false, in_flight = false;
+	int64_t launches = 0;
+};
+
+template <typename T>
+int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out) {
+	if (!out) return fail(B200LP_ERR_ARG, "out is NULL");
+	*out = nullptr;
+	if (m <= 0 || n <= 0 || m > n) return fail(B200LP_ERR_ARG, "need 0 < m <= n (v4:402)");
+	if (n >= ((int64_t)1 << 31)) return fail(B200LP_ERR_ARG, "n must fit a 32-bit basis index");
+	b200lp_options o;
+	if (opt) o = *opt; else b200lp_default_options(&o);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(B200LP_ERR_NO_GPU, "no CUDA device: the engine has no CPU fallback");
+	}
+	if (o.device < 0 || o.device >= ndev) return fail(B200LP_ERR_ARG, "device ordinal out of range");
+	auto* e = new Engine<T>(m, n, o);
+	int rc = e->init();
+	if (rc) { delete e; return rc; }
+	*out = e;
+	return B200LP_OK;
+}
+
+template <typename T>
+int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b200lp_options* opt,
+		T* x_b, int32_t* b_ixs, int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	if (!A || !b || !c) return fail(B200LP_ERR_ARG, "A, b, c must not be NULL");
+	b200lp_options o;
+	if (opt) o = *opt; else b200lp_default_options(&o);
+	b200lp_engine* e = nullptr;
+	int rc = create_engine<T>(m, n, &o, &e);
+	if (rc) return rc;
+	b200lp_result r;
+	std::memset(&r, 0, sizeof(r));
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	do {
+		if ((rc = e->upload(A, b, c))) break;
+		if ((rc = e->run_async(o.max_iter))) break;
+		if ((rc = e->wait(&r))) break;
+		cudaEventCreate(&t0);
+		cudaEventCreate(&t1);
+		cudaEventRecord(t0, e->stream);
+		if ((rc = e->download(x_b, b_ixs, nullptr))) break;
+		if (trace_pq && trace_cap > 0 && (rc = e->download_trace(trace_pq, trace_cap, nullptr))) break;
+		cudaEventRecord(t1, e->stream);
+		cudaEventSynchronize(t1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, t0, t1);
+		r.ms_download = ms;
+	} while (0);
+	if (t0) cudaEventDestroy(t0);
+	if (t1) cudaEventDestroy(t1);
+	if (res) *res = r;
+	delete e;
+	return rc;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+void b200lp_default_options(b200lp_options* opt) {
+	if (!opt) return;
+	std::memset(opt, 0, sizeof(*opt));
+	opt->eps = 1e-4;      // v4:18
+	opt->max_iter = 5;    // v4:19
+	opt->device = 0;
+	opt->check_slack = 1;
+}
+
+int b200lp_solve_f64(const double* A, const double* b, const double* c, int64_t m, int64_t n,
+		const b200lp_options* opt, double* x_b, int32_t* b_ixs, int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	return solve_once<double>(A, b, c, m, n, opt, x_b, b_ixs, trace_pq, trace_cap, res);
+}
+
+int b200lp_solve_f32(const float* A, const float* b, const float* c, int64_t m, int64_t n,
+		const b200lp_options* opt, float* x_b, int32_t* b_ixs, int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	return solve_once<float>(A, b, c, m, n, opt, x_b, b_ixs, trace_pq, trace_cap, res);
+}
+
+int b200lp_create(int32_t dtype, int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out) {
+	if (dtype == B200LP_F64) return create_engine<double>(m, n, opt, out);
+	if (dtype == B200LP_F32) return create_engine<float>(m, n, opt, out);
+	return fail(B200LP_ERR_ARG, "dtype must be B200LP_F32 or B200LP_F64");
+}
+
+#define NEED(e) do { if (!(e)) return fail(B200LP_ERR_ARG, "engine is NULL"); } while (0)
+
+int b200lp_destroy(b200lp_engine* e) { delete e; return B200LP_OK; }
+int b200lp_upload(b200lp_engine* e, const void* A, const void* b, const void* c) {
+	NEED(e);
+	if (!A || !b || !c) return fail(B200LP_ERR_ARG, "A, b, c must not be NULL");
+	return e->upload(A, b, c);
+}
+int b200lp_generate_dense(b200lp_engine* e, uint64_t seed) { NEED(e); return e->generate_dense(seed); }
+int b200lp_reset(b200lp_engine* e) { NEED(e); return e->reset(); }
+int b200lp_run(b200lp_engine* e, int64_t iterations, b200lp_result* res) {
+	NEED(e);
+	int rc = e->run_async(iterations);
+	if (rc) return rc;
+	return e->wait(res);
+}
+int b200lp_run_async(b200lp_engine* e, int64_t iterations) { NEED(e); return e->run_async(iterations); }
+int b200lp_wait(b200lp_engine* e, b200lp_result* res) { NEED(e); return e->wait(res); }
+int b200lp_download(b200lp_engine* e, void* x_b, int32_t* b_ixs, void* y) { NEED(e); return e->download(x_b, b_ixs, y); }
+int b200lp_download_binv(b200lp_engine* e, void* Binv) { NEED(e); if (!Binv) return fail(B200LP_ERR_ARG, "Binv is NULL"); return e->download_binv(Binv); }
+int b200lp_download_trace(b200lp_engine* e, int32_t* pq, int64_t cap, int64_t* n_out) { NEED(e); return e->download_trace(pq, cap, n_out); }
+int b200lp_phase_price(b200lp_engine* e, int64_t* p, double* min_e) { NEED(e); return e->phase_price(p, min_e); }
+int b200lp_phase_update_ftran(b200lp_engine* e, int64_t p) { NEED(e); return e->phase_update_ftran(p); }
+int b200lp_phase_ratio(b200lp_engine* e, int64_t* q, int64_t* eligible) { NEED(e); return e->phase_ratio(q, eligible); }
+int b200lp_phase_pivot_update(b200lp_engine* e, int64_t p, int64_t q) { NEED(e); return e->phase_pivot_update(p, q); }
+int b200lp_download_vector(b200lp_engine* e, int32_t which, void* out) { NEED(e); return e->download_vector(which, out); }
+
+void* b200lp_stream(b200lp_engine* e) { return e ? (void*)e->stream : nullptr; }
+int b200lp_grid_ctas(b200lp_engine* e) { return e ? e->grid : 0; }
+int b200lp_dense_columns(b200lp_engine* e) { return e ? (int)e->ns : 0; }
+int64_t b200lp_bytes_per_pivot(b200lp_engine* e) { return e ? e->bytes_per_pivot() : 0; }
+const char* b200lp_last_error(void) { return g_err.c_str(); }
+const char* b200lp_version(void) { return "b200lp 0.1 (sm_100a)"; }
+
+} // extern "C"

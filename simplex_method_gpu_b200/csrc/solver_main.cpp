@@ -1,0 +1,175 @@
+// CLI with the driver contract of the reference's main() (src/v4_cub_reduction.cu:384-474):
+//   solver.out <lp.txt> [--f64] [--eps E] [--max-iter N] [--device D]
+// Same input text format (v4:401-420), same stdout: one "# Iteration k" line per
+// iteration (v4:287), the result block (v4:426-445) and the timing block
+// (v4:456-471, same labels and number format).  Defaults reproduce the reference's
+// compile-time constants: real = float, EPS = 1e-4, MAX_ITER = 5 (v4:12, 18-19).
+// All numerics run in libb200lp.so through the C ABI.
+#include "b200lp.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+
+using Clock = std::chrono::high_resolution_clock;
+
+static double secs(Clock::time_point a, Clock::time_point b) {
+	return std::chrono::duration<double>(b - a).count();
+}
+
+// "<label>: " right-aligned in 19 columns, seconds with 2 decimals in 6 (v4:151-157)
+static void print_time(const char* label, double s) {
+	std::cout << std::setw(19) << (std::string(label) + ": ");
+	std::cout << std::fixed << std::setprecision(2) << std::setw(6) << s << '\n';
+}
+
+struct Tokens {
+	std::vector<char> buf;
+	char* cur = nullptr;
+	bool load(const char* path) {
+		FILE* f = std::fopen(path, "rb");
+		if (!f) return false;
+		std::fseek(f, 0, SEEK_END);
+		long sz = std::ftell(f);
+		std::fseek(f, 0, SEEK_SET);
+		buf.resize((size_t)sz + 1);
+		size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+		std::fclose(f);
+		buf[got] = 0;
+		cur = buf.data();
+		return true;
+	}
+	bool next_long(long& v) {
+		char* end;
+		v = std::strtol(cur, &end, 10);
+		if (end == cur) return false;
+		cur = end;
+		return true;
+	}
+	bool next_double(double& v) {
+		char* end;
+		v = std::strtod(cur, &end);
+		if (end == cur) return false;
+		cur = end;
+		return true;
+	}
+};
+
+// row-major text -> column-major storage (v4:94-104)
+template <typename T>
+static bool load_matrix(Tokens& tk, std::vector<T>& a, long rows, long cols, const char* name) {
+	for (long i = 0; i < rows; ++i)
+		for (long j = 0; j < cols; ++j) {
+			double v;
+			if (!tk.next_double(v)) {
+				std::cerr << "Failed to read (" << i << "," << j << ") for " << name << "\n";
+				return false;
+			}
+			a[(size_t)i + (size_t)j * rows] = (T)v;
+		}
+	return true;
+}
+
+template <typename T>
+static int run(Tokens& tk, long m, long n, b200lp_options opt, Clock::time_point t_start) {
+	auto t_host_alloc = Clock::now();
+	std::vector<T> A((size_t)m * n), b((size_t)m), c((size_t)n), x_b((size_t)m);
+	std::vector<int32_t> b_ixs((size_t)m);
+
+	auto t_read = Clock::now();
+	if (!load_matrix(tk, A, m, n, "A") || !load_matrix(tk, b, m, 1, "b") || !load_matrix(tk, c, 1, n, "c"))
+		return EXIT_FAILURE;
+
+	auto t_solve = Clock::now();
+	b200lp_result r;
+	int rc;
+	if (sizeof(T) == 8)
+		rc = b200lp_solve_f64((const double*)A.data(), (const double*)b.data(), (const double*)c.data(), m, n, &opt,
+				(double*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
+	else
+		rc = b200lp_solve_f32((const float*)A.data(), (const float*)b.data(), (const float*)c.data(), m, n, &opt,
+				(float*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
+	if (rc != B200LP_OK) {
+		std::cerr << "b200lp failed (" << rc << "): " << b200lp_last_error() << "\n";
+		return EXIT_FAILURE;
+	}
+
+	auto t_print = Clock::now();
+	for (int64_t i = 0; i < r.iterations; ++i) std::cout << "# Iteration " << (i + 1) << '\n';
+	switch (r.status) {
+	case B200LP_STATUS_OPTIMUM:
+		std::cout << "Optimum found: " << (T)r.z << '\n';
+		for (long i = 0; i < m; ++i) std::cout << "\tx_" << b_ixs[i] << " = " << x_b[i] << "\n";
+		break;
+	case B200LP_STATUS_UNBOUNDED: std::cout << "Problem unbounded.\n"; break;
+	case B200LP_STATUS_THETA_OVERFLOW: std::cout << "Theta overflow.\n"; break;
+	default: std::cout << "MAX_ITER exceeded.\n"; break;
+	}
+	std::cout << '\n';
+
+	auto t_free = Clock::now();
+	A.clear(); A.shrink_to_fit();
+	auto t_end = Clock::now();
+
+	// the pivot loop is one fused kernel, so the reference's per-phase host timers
+	// (y / p / B_inv / x_b, launch overhead only there, v4:293-357) have no counterpart;
+	// "Solve call" carries the whole device time
+	print_time("Total", secs(t_start, t_end));
+	std::cout << '\n';
+	print_time("y", 0.0);
+	print_time("p", 0.0);
+	print_time("B_inv", r.ms_solve * 1e-3);
+	print_time("x_b", 0.0);
+	std::cout << '\n';
+	print_time("Alloc", 0.0);
+	print_time("Init", r.ms_upload * 1e-3);
+	print_time("Dealloc", 0.0);
+	std::cout << '\n';
+	print_time("Host alloc", secs(t_host_alloc, t_read));
+	print_time("Read file", secs(t_read, t_solve));
+	print_time("Solve call", secs(t_solve, t_print));
+	print_time("Print result", secs(t_print, t_free));
+	print_time("Host free", secs(t_free, t_end));
+	return 0;
+}
+
+int main(int argc, char* argv[]) {
+	std::ios_base::sync_with_stdio(false);
+	if (argc < 2) {
+		std::cerr << "Please, specify an input file.\n";
+		return 1;
+	}
+	auto t_start = Clock::now();
+
+	b200lp_options opt;
+	b200lp_default_options(&opt);
+	bool f64 = false;
+	for (int i = 2; i < argc; ++i) {
+		if (!std::strcmp(argv[i], "--f64")) f64 = true;
+		else if (!std::strcmp(argv[i], "--f32")) f64 = false;
+		else if (!std::strcmp(argv[i], "--eps") && i + 1 < argc) opt.eps = std::atof(argv[++i]);
+		else if (!std::strcmp(argv[i], "--max-iter") && i + 1 < argc) opt.max_iter = std::atoll(argv[++i]);
+		else if (!std::strcmp(argv[i], "--device") && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+		else {
+			std::cerr << "Unknown option " << argv[i] << "\n";
+			return 1;
+		}
+	}
+
+	Tokens tk;
+	if (!tk.load(argv[1])) {
+		std::cerr << "Could not open " << argv[1] << ".\n";
+		return 1;
+	}
+	long m = 0, n = 0;
+	if (!tk.next_long(m) || !tk.next_long(n) || m > n || m <= 0) {
+		std::cerr << "Either failed to read m and n, or m > n.\n";
+		return 1;
+	}
+	return f64 ? run<double>(tk, m, n, opt, t_start) : run<float>(tk, m, n, opt, t_start);
+}

@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's solver interface for the hot path.
+
+Reference contract (src/v4_cub_reduction.cu):
+  * ``solve(A, b, c, x_b, b_ixs, m, n, t) -> (z, SolveStatus)``           v4:219
+  * LP text format ``m n`` / A (m rows x n) / b / c, slack block last     v4:401-420, input/sample.txt
+  * result printing                                                        v4:426-445
+Everything numeric happens in libb200lp.so (hand-written sm_100a kernels); this
+module only marshals numpy arrays across the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import io
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+class SolveStatus(enum.IntEnum):
+    """`enum class SolveStatus` (v4:49-54)."""
+    MaxIter = 0
+    OptimumFound = 1
+    Unbounded = 2
+    ThetaOverflow = 3
+
+
+# reference compile-time constants (v4:12, 18-19)
+REAL = np.float32
+EPS = 1e-4
+MAX_ITER = 5
+
+
+@dataclass
+class Solution:
+    z: float
+    status: SolveStatus
+    x_b: np.ndarray          # basis-ordered values (v4:366)
+    b_ixs: np.ndarray        # basis-ordered column indices (v4:367)
+    iterations: int          # "# Iteration k" lines the reference prints (v4:287)
+    pivots: int
+    trace: np.ndarray        # (pivots, 2) int32: entering column p, leaving row q
+    ms_upload: float = 0.0
+    ms_solve: float = 0.0
+    ms_download: float = 0.0
+    kernel_launches: int = 0
+    min_reduced_cost: float = 0.0
+
+    def x(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=self.x_b.dtype)
+        out[self.b_ixs] = self.x_b
+        return out
+
+
+def _dtype_code(dt) -> int:
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return capi.F32
+    if dt == np.float64:
+        return capi.F64
+    raise TypeError(f"real must be float32 or float64, got {dt}")
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _prep(A, b, c, dtype):
+    dt = np.dtype(dtype if dtype is not None else A.dtype)
+    _dtype_code(dt)
+    A = np.asfortranarray(A, dtype=dt)      # column-major like the reference (v4:59-60, 98)
+    if A.ndim != 2:
+        raise ValueError("A must be a matrix")
+    m, n = A.shape
+    b = np.ascontiguousarray(b, dtype=dt).reshape(-1)
+    c = np.ascontiguousarray(c, dtype=dt).reshape(-1)
+    if b.size != m or c.size != n:
+        raise ValueError(f"shape mismatch: A is {m}x{n}, b has {b.size}, c has {c.size}")
+    if m > n:
+        raise ValueError("Either failed to read m and n, or m > n.")   # v4:403
+    return A, b, c, m, n, dt
+
+
+def solve(A, b, c, eps: float = EPS, max_iter: int = MAX_ITER, dtype=None, device: int = 0,
+          trace_cap: int | None = None, **opts) -> Solution:
+    """Drop-in for the reference's ``solve()`` (v4:219): host arrays in, host arrays out."""
+    A, b, c, m, n, dt = _prep(A, b, c, dtype)
+    L = capi.lib()
+    o = capi.default_options(eps=eps, max_iter=int(max_iter), device=device, **opts)
+    cap = int(trace_cap if trace_cap is not None else min(int(max_iter), 1 << 22))
+    x_b = np.zeros(m, dt)
+    b_ixs = np.zeros(m, np.int32)
+    trace = np.full((max(cap, 1), 2), -1, np.int32)
+    res = capi.Result()
+    fn = L.b200lp_solve_f64 if dt == np.float64 else L.b200lp_solve_f32
+    capi.check(fn(_vp(A), _vp(b), _vp(c), m, n, C.byref(o), _vp(x_b), _vp(b_ixs), _vp(trace), cap, C.byref(res)))
+    k = min(res.pivots, cap)
+    return Solution(res.z, SolveStatus(res.status), x_b, b_ixs, res.iterations, res.pivots, trace[:k].copy(),
+                    res.ms_upload, res.ms_solve, res.ms_download, res.kernel_launches, res.min_reduced_cost)
+
+
+class Engine:
+    """Handle API: device state survives between calls (benchmark windows, phase tests)."""
+
+    def __init__(self, m: int, n: int, dtype=np.float64, eps: float = EPS, max_iter: int = MAX_ITER,
+                 device: int = 0, **opts):
+        self.m, self.n, self.dtype = int(m), int(n), np.dtype(dtype)
+        self._L = capi.lib()
+        self._o = capi.default_options(eps=eps, max_iter=int(max_iter), device=device, **opts)
+        self._h = C.c_void_p()
+        capi.check(self._L.b200lp_create(_dtype_code(self.dtype), self.m, self.n, C.byref(self._o), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.b200lp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data
+    def upload(self, A, b, c):
+        A, b, c, m, n, dt = _prep(A, b, c, self.dtype)
+        if (m, n) != (self.m, self.n):
+            raise ValueError("problem size differs from the engine's")
+        capi.check(self._L.b200lp_upload(self._h, _vp(A), _vp(b), _vp(c)))
+
+    def upload_raw(self, A_ptr: int, b_ptr: int, c_ptr: int):
+        """Host pointers of the engine's dtype (e.g. pinned torch tensors), no copies made here."""
+        capi.check(self._L.b200lp_upload(self._h, C.c_void_p(A_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr)))
+
+    def generate_dense(self, seed: int = 1):
+        capi.check(self._L.b200lp_generate_dense(self._h, seed))
+
+    def reset(self):
+        capi.check(self._L.b200lp_reset(self._h))
+
+    # -- loop
+    def _result(self, res) -> dict:
+        return {"status": SolveStatus(res.status), "iterations": res.iterations, "pivots": res.pivots, "z": res.z,
+                "min_reduced_cost": res.min_reduced_cost, "ms_solve": res.ms_solve, "ms_upload": res.ms_upload,
+                "kernel_launches": res.kernel_launches}
+
+    def run(self, iterations: int) -> dict:
+        res = capi.Result()
+        capi.check(self._L.b200lp_run(self._h, int(iterations), C.byref(res)))
+        return self._result(res)
+
+    def run_async(self, iterations: int):
+        capi.check(self._L.b200lp_run_async(self._h, int(iterations)))
+
+    def wait(self) -> dict:
+        res = capi.Result()
+        capi.check(self._L.b200lp_wait(self._h, C.byref(res)))
+        return self._result(res)
+
+    # -- results
+    def download(self):
+        x_b = np.zeros(self.m, self.dtype)
+        y = np.zeros(self.m, self.dtype)
+        b_ixs = np.zeros(self.m, np.int32)
+        capi.check(self._L.b200lp_download(self._h, _vp(x_b), _vp(b_ixs), _vp(y)))
+        return x_b, b_ixs, y
+
+    def download_binv(self) -> np.ndarray:
+        B = np.zeros((self.m, self.m), self.dtype, order="F")
+        capi.check(self._L.b200lp_download_binv(self._h, _vp(B)))
+        return B
+
+    def trace(self, cap: int = 1 << 22) -> np.ndarray:
+        buf = np.full((cap, 2), -1, np.int32)
+        k = C.c_int64(0)
+        capi.check(self._L.b200lp_download_trace(self._h, _vp(buf), cap, C.byref(k)))
+        return buf[:k.value].copy()
+
+    def vector(self, name: str) -> np.ndarray:
+        which = {"alpha": 0, "E_q": 1, "row_q": 2, "x_b": 3, "y": 4, "c_b": 5}[name]
+        out = np.zeros(self.m, self.dtype)
+        capi.check(self._L.b200lp_download_vector(self._h, which, _vp(out)))
+        return out
+
+    # -- single phases
+    def phase_price(self):
+        p, mn = C.c_int64(0), C.c_double(0)
+        capi.check(self._L.b200lp_phase_price(self._h, C.byref(p), C.byref(mn)))
+        return p.value, mn.value
+
+    def phase_update_ftran(self, p: int):
+        capi.check(self._L.b200lp_phase_update_ftran(self._h, int(p)))
+
+    def phase_ratio(self):
+        q, el = C.c_int64(0), C.c_int64(0)
+        capi.check(self._L.b200lp_phase_ratio(self._h, C.byref(q), C.byref(el)))
+        return q.value, el.value
+
+    def phase_pivot_update(self, p: int, q: int):
+        capi.check(self._L.b200lp_phase_pivot_update(self._h, int(p), int(q)))
+
+    # -- introspection
+    @property
+    def stream(self) -> int:
+        return int(self._L.b200lp_stream(self._h) or 0)
+
+    @property
+    def grid_ctas(self) -> int:
+        return self._L.b200lp_grid_ctas(self._h)
+
+    @property
+    def dense_columns(self) -> int:
+        return self._L.b200lp_dense_columns(self._h)
+
+    @property
+    def bytes_per_pivot(self) -> int:
+        return self._L.b200lp_bytes_per_pivot(self._h)
+
+
+# ---------------------------------------------------------------- text format + printing
+
+def read_lp(path_or_file, dtype=REAL):
+    """Parse the reference's LP text format (v4:401-420, input/sample.txt): ``m n``,
+    A as m rows of n numbers, b (m), c (n); anything after that is ignored."""
+    if hasattr(path_or_file, "read"):
+        text = path_or_file.read()
+    else:
+        with open(path_or_file, "r") as f:
+            text = f.read()
+    toks = text.split()
+    try:
+        m, n = int(toks[0]), int(toks[1])
+    except (IndexError, ValueError):
+        raise ValueError("Either failed to read m and n, or m > n.")      # v4:403
+    if m > n:
+        raise ValueError("Either failed to read m and n, or m > n.")
+    need = m * n + m + n
+    vals = []
+    for k, t in enumerate(toks[2:2 + need]):
+        try:
+            vals.append(float(t))
+        except ValueError:
+            break
+    if len(vals) < need:
+        k = len(vals)
+        if k < m * n:
+            raise ValueError(f"Failed to read ({k // n},{k % n}) for A")   # v4:99
+        if k < m * n + m:
+            raise ValueError(f"Failed to read ({k - m * n},0) for b")
+        raise ValueError(f"Failed to read (0,{k - m * n - m}) for c")
+    v = np.asarray(vals, dtype=np.float64)
+    A = np.asfortranarray(v[:m * n].reshape(m, n), dtype=dtype)              # row-major text -> col-major
+    b = v[m * n:m * n + m].astype(dtype)
+    c = v[m * n + m:].astype(dtype)
+    return A, b, c
+
+
+def write_lp(path, A, b, c):
+    m, n = A.shape
+    with open(path, "w") as f:
+        f.write(f"{m} {n}\n")
+        for i in range(m):
+            f.write(" ".join(repr(float(x)) for x in A[i]) + "\n")
+        f.write(" ".join(repr(float(x)) for x in b) + "\n")
+        f.write(" ".join(repr(float(x)) for x in c) + "\n")
+
+
+def _cxx_float(x) -> str:
+    """C++ ``ostream << real`` with default flags: %g with 6 significant digits."""
+    return "%g" % float(x)
+
+
+def format_result(sol: Solution) -> str:
+    """The reference's stdout up to the timing block (v4:287, 426-445)."""
+    out = io.StringIO()
+    for i in range(sol.iterations):
+        out.write(f"# Iteration {i + 1}\n")
+    if sol.status == SolveStatus.OptimumFound:
+        out.write(f"Optimum found: {_cxx_float(sol.z)}\n")
+        for ix, val in zip(sol.b_ixs, sol.x_b):
+            out.write(f"\tx_{int(ix)} = {_cxx_float(val)}\n")
+    elif sol.status == SolveStatus.Unbounded:
+        out.write("Problem unbounded.\n")
+    elif sol.status == SolveStatus.ThetaOverflow:
+        out.write("Theta overflow.\n")
+    else:
+        out.write("MAX_ITER exceeded.\n")
+    out.write("\n")
+    return out.getvalue()
