@@ -145,7 +145,7 @@ public:
 		if (!hA || ns_new != d.ns) {
 			if (hA) cudaFree(hA);
 			hA = nullptr;
-			if (ns_new > 0) CU(alloc(&hA, (size_t)ld * ns_new));
+			if (ns_new > 0) CU(cudaMalloc((void**)&hA, (size_t)ld * ns_new * sizeof(T)));
 			d.A = hA;
 			d.ns = ns_new;
 			ns = ns_new;
@@ -177,7 +177,7 @@ public:
 		if (!hA || ns_new != d.ns) {
 			if (hA) cudaFree(hA);
 			hA = nullptr;
-			if (ns_new > 0) CU(alloc(&hA, (size_t)d.ld * ns_new));
+			if (ns_new > 0) CU(cudaMalloc((void**)&hA, (size_t)d.ld * ns_new * sizeof(T)));
 			d.A = hA;
 			d.ns = ns_new;
 			ns = ns_new;
@@ -206,6 +206,10 @@ public:
 	int run_async(int64_t iters) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "run before upload/generate");
 		CU(cudaSetDevice(opt.device));
+		if (in_flight) {           // host mirror of the control block is stale until wait()
+			int rc = wait(nullptr);
+			if (rc) return rc;
+		}
 		in_flight = true;
 		if (hc.done || iters <= 0) {
 			CU(cudaEventRecord(ev0, stream));
@@ -372,8 +376,7 @@ private:
 
 	void release() {
 		if (stream) cudaStreamSynchronize(stream);
-		for (void* p : owned)
-			if (p != (void*)hA) cudaFree(p);
+		for (void* p : owned) cudaFree(p);
 		if (hA) cudaFree(hA);
 		owned.clear();
 		if (pinned) cudaFreeHost(pinned);

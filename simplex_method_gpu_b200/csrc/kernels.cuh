@@ -98,7 +98,7 @@ template <> struct Mem<double> {
 	// read-only stream (A): non-coherent path, do not allocate in L1
 	static __device__ __forceinline__ V ld_nc(const double* p) {
 		V v;
-		asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+		asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
 		return v;
 	}
 	// read-write stream (B^-1): coherent, do not allocate in L1
@@ -117,7 +117,7 @@ template <> struct Mem<float> {
 	using V = float4;
 	static __device__ __forceinline__ V ld_nc(const float* p) {
 		V v;
-		asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+		asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
 		return v;
 	}
 	static __device__ __forceinline__ V ld_stream(const float* p) {
@@ -257,7 +257,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts, lon
 #pragma unroll
 			for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
 
-#pragma unroll 2
+#pragma unroll 4
 		for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
 			const V yv = *reinterpret_cast<const V*>(d.y + i);
 			V av[PRICE_NC];
@@ -460,6 +460,7 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts, lon
 	long long elig = 0;
 	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
 		T a = __ldcg(d.alpha_part + i);
+#pragma unroll 8
 		for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ld + i);
 		d.alpha[i] = a;
 		if (a > T(0)) {
@@ -532,6 +533,7 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 	__syncthreads();
 	if (tid < 2) {
 		T a = T(0);
+#pragma unroll 8
 		for (int s = 0; s < d.nslice; ++s) a = a + __ldcg(d.dpart + (long long)tid * d.nslice + s);
 		if (tid == 1) a += d.c[p] - (T)__ldcg(&d.ctl->c_b_q);
 		sh.bc_s[tid] = (double)a;

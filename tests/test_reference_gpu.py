@@ -1,0 +1,100 @@
+"""GPU box only: the reference's OWN v4 build (oracle/_ref, produced from
+/root/reference by oracle/make_ref.sh) pins the CPU oracle and the engine.
+
+  v4_stock.out      the reference exactly as shipped (float, EPS 1e-4, MAX_ITER 5)
+  libv4ref_f64.so   v4 + the documented minimal patches, real = double
+Nothing here reads /root/reference at run time; the prebuilt binaries travel with the repo.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TIE = 1e-12
+
+
+def _need_ref(oracle, dtype=np.float64):
+    if not oracle.ref_available(dtype):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+
+
+def test_stock_reference_binary_on_sample_matches_cli(oracle, engine_lib):
+    """Byte-for-byte stdout parity with the unmodified reference up to the timing values."""
+    exe = oracle.ref_stock_binary()
+    if exe is None:
+        pytest.skip("oracle/_ref/v4_stock.out not built")
+    sample = os.path.join(GOLDEN, "sample.txt")
+    ref = subprocess.run([exe, sample], capture_output=True, text=True, timeout=300)
+    ours = subprocess.run([os.path.join(ROOT, "bin", "solver.out"), sample], capture_output=True, text=True, timeout=300)
+    assert ref.returncode == 0 and ours.returncode == 0, (ref.stderr, ours.stderr)
+    head = "# Iteration 1\n# Iteration 2\n# Iteration 3\nOptimum found: 9\n\tx_1 = 3\n\tx_0 = 1\n\n"
+    assert ours.stdout.startswith(head)
+
+    def timing_block(s):   # same labels, same layout, values differ
+        blk = s[s.index("\n\n") + 2:]
+        return [(ln.split(":")[0], len(ln)) for ln in blk.splitlines()]
+    assert timing_block(ref.stdout) == timing_block(ours.stdout)
+    if not ref.stdout.startswith(head):
+        # The shipped v4 sets CUBLAS_POINTER_MODE_DEVICE and then passes HOST stack scalars
+        # (v4:225, 243, 289-290): on a box without pageable-memory access the GEMM never runs,
+        # `e` stays uninitialised and v4 reports a bogus optimum in iteration 1.  That is the
+        # reference's bug (fixed by patch P5 in make_ref.sh), not a parity failure of the engine.
+        assert ref.stdout.startswith("# Iteration 1\n")
+        pytest.xfail("stock v4 is broken on this box by its device-pointer-mode bug: " + ref.stdout.split("\n")[1])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_patched_reference_on_sample(oracle, dtype):
+    _need_ref(oracle, dtype)
+    import simplex_method_gpu_b200 as lp
+    A, b, c = lp.read_lp(os.path.join(GOLDEN, "sample.txt"), dtype=dtype)
+    r = oracle.ref_solve(A, b, c, eps=1e-4, max_iter=5)
+    assert r.status == oracle.OPTIMUM and r.iterations == 3 and r.z == 9.0
+    assert r.trace_p.tolist() == [0, 1] and r.trace_q.tolist() == [1, 0]
+    assert r.b_ixs.tolist() == [1, 0] and r.x_b.tolist() == [3.0, 1.0]
+
+
+@pytest.mark.parametrize("m,n,seed", [(64, 128, 1), (256, 512, 1), (300, 700, 2), (1024, 2048, 1)])
+def test_oracle_and_engine_match_reference_f64(oracle, engine_lib, m, n, seed):
+    """The oracle is pinned by the reference itself, and the engine walks the same path."""
+    _need_ref(oracle)
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(m, n, seed)
+    ref = oracle.ref_solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    cpu = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    assert ref.status == oracle.OPTIMUM
+    for name, tp, tq, z, xb, bi, it in (("oracle", cpu.trace_p, cpu.trace_q, cpu.z, cpu.x_b, cpu.b_ixs, cpu.iterations),
+                                        ("engine", sol.trace[:, 0], sol.trace[:, 1], sol.z, sol.x_b, sol.b_ixs, sol.iterations)):
+        k = min(len(tp), len(ref.trace_p))
+        same = (tp[:k] == ref.trace_p[:k]) & (tq[:k] == ref.trace_q[:k])
+        if not same.all():
+            first = int(np.argmin(same))
+            gap = min(cpu.gap_p[first], cpu.gap_q[first])
+            assert gap <= TIE, f"{name}: diverges from the reference at pivot {first} with runner-up gap {gap:g}"
+        else:
+            assert len(tp) == len(ref.trace_p) and it == ref.iterations, name
+            assert np.array_equal(bi, ref.b_ixs), name
+            assert np.abs(xb - ref.x_b).max() <= 1e-9 * max(1.0, np.abs(ref.x_b).max()), name
+        assert abs(z - ref.z) <= 1e-9 * abs(ref.z), name
+
+
+def test_reference_exact_problems(oracle, engine_lib):
+    _need_ref(oracle)
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_klee_minty(10)
+    ref = oracle.ref_solve(A, b, c, eps=1e-4, max_iter=1 << 20)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20)
+    assert ref.status == oracle.OPTIMUM and ref.pivots == 1023 and ref.z == 5.0 ** 10
+    assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist()
+    assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs) and sol.z == ref.z
+    A, b, c, w = oracle.gen_assignment(16, 1)        # n - m > m: needs the v4:277 length fix
+    ref = oracle.ref_solve(A, b, c, eps=1e-4, max_iter=1 << 20)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20)
+    assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist()
+    assert sol.z == ref.z and np.array_equal(sol.x_b, ref.x_b)
