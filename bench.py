@@ -152,12 +152,11 @@ def run_b200_single(args, wl):
     # ---- end to end through the C ABI with host buffers ("e2e")
     e2e = None
     if not args.no_e2e:
-        import oracle
         A_pin = torch.empty((n, m), dtype=torch.float64, pin_memory=True)    # column-major m x n
         b_pin = torch.empty(m, dtype=torch.float64, pin_memory=True)
         c_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
         A_np = A_pin.numpy().T                                                # Fortran-ordered view
-        oracle.lib().lpgen_dense_f64(A_pin.data_ptr(), b_pin.data_ptr(), c_pin.data_ptr(), m, n, SEED)
+        lp.solver.lpgen_dense_into(A_pin.data_ptr(), b_pin.data_ptr(), c_pin.data_ptr(), m, n, 0, n, SEED)
         times, piv = [], 0
         for s in range(args.warmup + args.steps):
             torch.cuda.synchronize()

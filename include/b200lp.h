@@ -136,6 +136,34 @@ int b200lp_phase_pivot_update(b200lp_engine* e, int64_t p, int64_t q);
 /* device vectors for inspection: which = 0 alpha, 1 E_q, 2 row_q, 3 x_b, 4 y, 5 c_b (length m) */
 int b200lp_download_vector(b200lp_engine* e, int32_t which, void* out);
 
+/* ---- sharded engine: one process per GPU of one NVSwitch box ----
+ * B^-1 is row-block sharded, A column-block sharded, all O(m) vectors replicated; every
+ * rank runs the same persistent kernel and the three per-pivot exchanges (pricing
+ * candidates, FTRAN result slices, pivot row) are direct peer stores over NVLink into
+ * IPC-mapped mailboxes.  The reference is single-GPU (v4:219-380 has no peer, stream or
+ * NCCL call), so these entry points have no counterpart there.
+ * Call order on EVERY rank: create_sharded -> upload | generate_dense -> ipc_export ->
+ * (all-gather the handle blobs with any host transport) -> ipc_import -> run (same
+ * iteration count on all ranks) -> download.  Results are replicated and bit-identical
+ * to the single-GPU engine. */
+int b200lp_create_sharded(int32_t dtype, int64_t m, int64_t n, int32_t rank, int32_t nranks,
+		const b200lp_options* opt, b200lp_engine** out);
+int b200lp_ipc_handle_bytes(void);                       /* size of one rank's handle blob */
+int b200lp_ipc_export(b200lp_engine* e, void* out);      /* this rank's blob */
+int b200lp_ipc_import(b200lp_engine* e, const void* all, int32_t nranks); /* nranks blobs, rank order */
+int b200lp_shard_rows(b200lp_engine* e, int64_t* row0, int64_t* rows);    /* B^-1 rows owned here */
+int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols); /* structural columns of A owned here */
+/* H2D of this rank's column block only (col-major m x ncols, starting at column col0 of A);
+ * the caller vouches for the identity slack block, which is never transferred */
+int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int64_t ncols,
+		const void* b, const void* c);
+
+/* ---- synthetic input (bench / tests) ----
+ * Host-side twin of b200lp_generate_dense: columns [col0, col0 + ncols) of the full
+ * [A_s, I_m] matrix (col-major m x ncols) and, when non-NULL, b (m) and c (n). */
+int b200lp_lpgen_dense_host(int32_t dtype, void* A_cols, void* b, void* c, int64_t m, int64_t n,
+		int64_t col0, int64_t ncols, uint64_t seed);
+
 /* ---- introspection ---- */
 void*       b200lp_stream(b200lp_engine* e);     /* cudaStream_t the engine launches on */
 int         b200lp_grid_ctas(b200lp_engine* e);

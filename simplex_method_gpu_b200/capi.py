@@ -19,6 +19,8 @@ EXPORTS = [
     "b200lp_phase_update_ftran", "b200lp_phase_ratio", "b200lp_phase_pivot_update", "b200lp_download_vector",
     "b200lp_stream", "b200lp_grid_ctas", "b200lp_dense_columns", "b200lp_bytes_per_pivot",
     "b200lp_last_error", "b200lp_version",
+    "b200lp_create_sharded", "b200lp_ipc_handle_bytes", "b200lp_ipc_export", "b200lp_ipc_import", "b200lp_shard_rows",
+    "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
 ]
 
 
@@ -76,6 +78,14 @@ def lib() -> C.CDLL:
         "b200lp_grid_ctas": (C.c_int, [vp]),
         "b200lp_dense_columns": (C.c_int, [vp]),
         "b200lp_bytes_per_pivot": (i64, [vp]),
+        "b200lp_create_sharded": (C.c_int, [i32, i64, i64, i32, i32, PO, C.POINTER(vp)]),
+        "b200lp_ipc_handle_bytes": (C.c_int, []),
+        "b200lp_ipc_export": (C.c_int, [vp, vp]),
+        "b200lp_ipc_import": (C.c_int, [vp, vp, i32]),
+        "b200lp_shard_rows": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "b200lp_shard_columns": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "b200lp_upload_columns": (C.c_int, [vp, vp, i64, i64, vp, vp]),
+        "b200lp_lpgen_dense_host": (C.c_int, [i32, vp, vp, vp, i64, i64, i64, i64, C.c_uint64]),
         "b200lp_last_error": (C.c_char_p, []),
         "b200lp_version": (C.c_char_p, []),
     }

@@ -33,6 +33,8 @@ static int fail(int code, const std::string& msg) {
 struct b200lp_engine {
 	virtual ~b200lp_engine() {}
 	virtual int upload(const void* A, const void* b, const void* c) = 0;
+	virtual int upload_columns(const void* Acols, int64_t col0, int64_t ncols, const void* b, const void* c) = 0;
+	virtual int shard_columns(int64_t* col0, int64_t* ncols) = 0;
 	virtual int generate_dense(uint64_t seed) = 0;
 	virtual int reset() = 0;
 	virtual int run_async(int64_t iters) = 0;
@@ -46,7 +48,11 @@ struct b200lp_engine {
 	virtual int phase_pivot_update(int64_t p, int64_t q) = 0;
 	virtual int download_vector(int32_t which, void* out) = 0;
 	virtual int64_t bytes_per_pivot() const = 0;
+	virtual int ipc_export(void* out) = 0;
+	virtual int ipc_import(const void* all, int nranks) = 0;
+	virtual int shard_rows(int64_t* row0, int64_t* rows) = 0;
 	cudaStream_t stream = nullptr;
+	int rank = 0, nranks = 1;
 	int grid = 0;
 	long long ns = 0;
 	double ms_upload = 0;
@@ -57,13 +63,24 @@ namespace {
 template <typename T>
 class Engine final : public b200lp_engine {
 public:
-	Engine(int64_t m, int64_t n, const b200lp_options& o) : opt(o) {
+	Engine(int64_t m, int64_t n, const b200lp_options& o, int rank_, int nranks_) : opt(o) {
 		std::memset(&d, 0, sizeof(d));
 		std::memset(&hc, 0, sizeof(hc));
+		rank = rank_;
+		nranks = nranks_;
 		d.m = m;
 		d.n = n;
 		constexpr long long rowq = 32 * VecT<T>::N;
 		d.ld = (m + rowq - 1) / rowq * rowq;
+		// row blocks of B^-1: equal multiples of one warp-wide vector row, the tail ranks may own fewer (or no) rows
+		d.rank = rank;
+		d.nranks = nranks;
+		const long long rpr = ((d.ld + nranks - 1) / nranks + rowq - 1) / rowq * rowq;
+		for (int r = 0; r <= nranks; ++r) d.rowstart[r] = std::min<long long>(d.ld, (long long)r * rpr);
+		d.row0 = d.rowstart[rank];
+		d.ldb = d.rowstart[rank + 1] - d.rowstart[rank];
+		d.k0 = m * rank / nranks;
+		d.k1 = m * (rank + 1) / nranks;
 		d.nchunk = (int)((m + CHUNK - 1) / CHUNK);
 		d.nslice = (int)((m + SLICE - 1) / SLICE);
 		d.eps = sizeof(T) == 4 ? (double)(float)o.eps : o.eps;
@@ -86,15 +103,22 @@ public:
 		CU(cudaEventCreate(&ev2));
 
 		const size_t ld = (size_t)d.ld, m = (size_t)d.m;
-		CU(alloc(&d.B, ld * m));
-		T* vecs[8];
+		CU(alloc(&d.B, (size_t)d.ldb * m));
+		T* vecs[6];
 		for (auto& v : vecs) CU(alloc(&v, ld));
 		d.b = vecs[0]; hb = vecs[0];
-		d.y = vecs[1]; d.x_b = vecs[2]; d.c_b = vecs[3]; d.alpha = vecs[4]; d.E_q = vecs[5]; d.row_q = vecs[6];
-		spare = vecs[7];
+		d.y = vecs[1]; d.x_b = vecs[2]; d.c_b = vecs[3]; d.E_q = vecs[4]; d.acol = vecs[5];
+		// mailbox: [XHdr][alpha ld][row_q ld]; peers store into it in sharded mode (IPC-exported)
+		mbox_bytes = sizeof(XHdr) + 2 * ld * sizeof(T);
+		CU(alloc(&mbox, mbox_bytes));
+		CU(cudaMemsetAsync(mbox, 0, mbox_bytes, stream));
+		d.alpha = reinterpret_cast<T*>(mbox + sizeof(XHdr));
+		d.row_q = d.alpha + ld;
+		for (int r = 0; r < MAXR; ++r) { d.mbox_peer[r] = nullptr; d.A_peer[r] = nullptr; }
+		d.mbox_peer[rank] = mbox;
 		CU(alloc(&hcst, (size_t)d.n));
 		d.c = hcst;
-		CU(alloc(&d.alpha_part, (size_t)d.nchunk * ld));
+		CU(alloc(&d.alpha_part, (size_t)d.nchunk * (size_t)d.ldb));
 		CU(alloc(&d.dpart, (size_t)2 * d.nslice));
 		CU(alloc(&d.b_ixs, m));
 		CU(alloc(&d.ctl, 1));
@@ -104,10 +128,11 @@ public:
 
 		// persistent grid: co-resident CTAs only (cooperative launch)
 		int occ = 0;
-		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, 0));
+		if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, 0));
+		else            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, 0));
 		if (occ < 1) return fail(B200LP_ERR_CUDA, "persistent kernel does not fit on an SM");
 		max_grid = occ * num_sms;
-		const double work = (double)d.ld * (double)d.n;
+		const double work = (double)d.ld * (double)d.n / nranks;
 		int g;
 		if (opt.grid_ctas > 0) g = opt.grid_ctas;
 		else if (work <= 64.0 * 1024) g = 1;                       // tiny LPs: barriers are pure latency
@@ -121,10 +146,11 @@ public:
 		wc = 8;
 		for (int cand_wc : {1, 2, 4, 8}) {
 			const long long tr = (long long)(NWARP / cand_wc) * 32 * VecT<T>::N;
-			const long long tiles = (d.ld + tr - 1) / tr * d.nchunk;
+			const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
 			if (tiles >= grid) { wc = cand_wc; break; }
 		}
 		if (opt.tile_shape == 1 || opt.tile_shape == 2 || opt.tile_shape == 4 || opt.tile_shape == 8) wc = opt.tile_shape;
+		if (nranks > 1 && wc != 1) wc = 8;       // the sharded kernel is instantiated for the two extreme shapes
 		return B200LP_OK;
 	}
 
@@ -132,32 +158,40 @@ public:
 
 	int upload(const void* Av, const void* bv, const void* cv) override {
 		const T* A = static_cast<const T*>(Av);
-		const T* b = static_cast<const T*>(bv);
-		const T* c = static_cast<const T*>(cv);
-		const long long m = d.m, n = d.n, ld = d.ld;
-		CU(cudaSetDevice(opt.device));
-
+		const long long m = d.m, n = d.n;
 		// Is the last m x m block the identity the reference assumes (v4:272)?  If so
 		// those columns are priced and FTRAN'd as unit vectors and never stored.
 		bool slack_ok = true;
 		if (opt.check_slack) slack_ok = host_is_identity(A + (size_t)(n - m) * m, m);
-		const long long ns_new = slack_ok ? n - m : n;
-		if (!hA || ns_new != d.ns) {
-			if (hA) cudaFree(hA);
-			hA = nullptr;
-			if (ns_new > 0) CU(cudaMalloc((void**)&hA, (size_t)ld * ns_new * sizeof(T)));
-			d.A = hA;
-			d.ns = ns_new;
-			ns = ns_new;
-		}
+		CU(cudaSetDevice(opt.device));
+		CU(set_columns(slack_ok ? n - m : n));
+		return upload_block(A + (size_t)d.col0 * m, bv, cv);
+	}
+
+	// sharded front door: the caller hands over only this rank's structural columns
+	// [col0, col0 + ncols) (column-major m x ncols) and vouches for the identity slack block
+	int upload_columns(const void* Acols, int64_t col0, int64_t ncols, const void* bv, const void* cv) override {
+		CU(cudaSetDevice(opt.device));
+		CU(set_columns(d.n - d.m));
+		if (col0 != d.col0 || ncols != d.nsl)
+			return fail(B200LP_ERR_ARG, "upload_columns: block is not this rank's column shard (see b200lp_shard_columns)");
+		return upload_block(Acols, bv, cv);
+	}
+
+	int upload_block(const void* Av, const void* bv, const void* cv) {
+		const T* A = static_cast<const T*>(Av);          // first column of this rank's block
+		const T* b = static_cast<const T*>(bv);
+		const T* c = static_cast<const T*>(cv);
+		const long long m = d.m, n = d.n, ld = d.ld;
 		CU(cudaEventRecord(ev0, stream));
-		if (d.ns > 0)
-			CU(cudaMemcpy2DAsync(hA, ld * sizeof(T), A, m * sizeof(T), m * sizeof(T), (size_t)d.ns, cudaMemcpyHostToDevice, stream));
+		if (d.nsl > 0)
+			CU(cudaMemcpy2DAsync(hA, ld * sizeof(T), A, m * sizeof(T), m * sizeof(T), (size_t)d.nsl,
+				cudaMemcpyHostToDevice, stream));
 		CU(cudaMemsetAsync(hb, 0, ld * sizeof(T), stream));
 		CU(cudaMemcpyAsync(hb, b, m * sizeof(T), cudaMemcpyHostToDevice, stream));
 		CU(cudaMemcpyAsync(hcst, c, n * sizeof(T), cudaMemcpyHostToDevice, stream));
-		if (ld > m && d.ns > 0) {
-			k_zero_pad<T><<<num_sms * 4, 256, 0, stream>>>(hA, m, ld, d.ns);
+		if (ld > m && d.nsl > 0) {
+			k_zero_pad<T><<<num_sms * 4, 256, 0, stream>>>(hA, m, ld, d.nsl);
 			launches++;
 		}
 		CU(cudaEventRecord(ev1, stream));
@@ -173,16 +207,8 @@ public:
 
 	int generate_dense(uint64_t seed) override {
 		CU(cudaSetDevice(opt.device));
-		const long long ns_new = d.n - d.m;
-		if (!hA || ns_new != d.ns) {
-			if (hA) cudaFree(hA);
-			hA = nullptr;
-			if (ns_new > 0) CU(cudaMalloc((void**)&hA, (size_t)d.ld * ns_new * sizeof(T)));
-			d.A = hA;
-			d.ns = ns_new;
-			ns = ns_new;
-		}
-		k_generate_dense<T><<<num_sms * 8, 256, 0, stream>>>(hA, hb, hcst, d.m, d.n, d.ns, d.ld, seed);
+		CU(set_columns(d.n - d.m));
+		k_generate_dense<T><<<num_sms * 8, 256, 0, stream>>>(hA, hb, hcst, d.m, d.n, d.ns, d.ld, seed, d.col0, d.nsl);
 		launches++;
 		CU(cudaGetLastError());
 		have_data = true;
@@ -195,9 +221,10 @@ public:
 		k_reset<T><<<num_sms * 8, 256, 0, stream>>>(d);
 		launches++;
 		CU(cudaGetLastError());
+		const unsigned long long xe = hc.xepoch;    // the peer-barrier epoch outlives a reset
 		std::memset(&hc, 0, sizeof(hc));
-		CU(cudaMemsetAsync(d.ctl, 0, sizeof(Ctl), stream));
-		CU(cudaStreamSynchronize(stream));
+		hc.xepoch = xe;
+		CU(push_ctl());
 		return B200LP_OK;
 	}
 
@@ -216,15 +243,21 @@ public:
 			CU(cudaEventRecord(ev1, stream));
 			return B200LP_OK;
 		}
-		if (opt.mode == 1) return run_phases(iters);
+		if (opt.mode == 1 && nranks == 1) return run_phases(iters);
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
 		CU(cudaEventRecord(ev0, stream));
 		void* args[] = {&d};
-		const void* fn = wc == 1 ? (const void*)simplex_persistent<T, 1>
-		               : wc == 2 ? (const void*)simplex_persistent<T, 2>
-		               : wc == 4 ? (const void*)simplex_persistent<T, 4>
-		                         : (const void*)simplex_persistent<T, 8>;
+		const void* fn;
+		if (nranks > 1) {
+			if (!peers_mapped) return fail(B200LP_ERR_STATE, "sharded engine: ipc_import has not been called");
+			fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1> : (const void*)simplex_persistent_sharded<T, 8>;
+		} else {
+			fn = wc == 1 ? (const void*)simplex_persistent<T, 1>
+			   : wc == 2 ? (const void*)simplex_persistent<T, 2>
+			   : wc == 4 ? (const void*)simplex_persistent<T, 4>
+			             : (const void*)simplex_persistent<T, 8>;
+		}
 		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, 0, stream));
 		launches++;
 		CU(cudaEventRecord(ev1, stream));
@@ -241,6 +274,7 @@ public:
 			CU(pull_ctl());
 		}
 		in_flight = false;
+		if (hc.bad) return fail(B200LP_ERR_CUDA, "sharded engine: a peer GPU did not reach the exchange barrier within 20 s");
 		if (res) {
 			std::memset(res, 0, sizeof(*res));
 			res->status = hc.status;
@@ -276,7 +310,10 @@ public:
 			CU(push_ctl());
 		}
 		CU(cudaStreamSynchronize(stream));
-		CU(cudaMemcpy2D(Binv, d.m * sizeof(T), d.B, d.ld * sizeof(T), d.m * sizeof(T), (size_t)d.m, cudaMemcpyDeviceToHost));
+		// the local row block [row0, row0 + rows) as a rows x m column-major matrix (all of B^-1 on one GPU)
+		const long long rows = std::max<long long>(0, std::min<long long>(d.m, d.row0 + d.ldb) - d.row0);
+		if (rows > 0)
+			CU(cudaMemcpy2D(Binv, rows * sizeof(T), d.B, d.ldb * sizeof(T), rows * sizeof(T), (size_t)d.m, cudaMemcpyDeviceToHost));
 		return B200LP_OK;
 	}
 
@@ -303,6 +340,7 @@ public:
 
 	int phase_price(int64_t* p, double* min_e) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
 		CU(cudaSetDevice(opt.device));
 		k_price<T><<<grid, NT, 0, stream>>>(d);
 		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 0);
@@ -316,6 +354,7 @@ public:
 
 	int phase_update_ftran(int64_t p) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
 		if (p < 0 || p >= d.n) return fail(B200LP_ERR_ARG, "entering column out of range");
 		CU(cudaSetDevice(opt.device));
 		launch_update_ftran(hc.pending != 0, true, p);
@@ -328,6 +367,7 @@ public:
 
 	int phase_ratio(int64_t* q, int64_t* eligible) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
 		CU(cudaSetDevice(opt.device));
 		k_ratio<T><<<grid, NT, 0, stream>>>(d);
 		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 1);
@@ -343,6 +383,7 @@ public:
 
 	int phase_pivot_update(int64_t p, int64_t q) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
 		if (p < 0 || p >= d.n || q < 0 || q >= d.m) return fail(B200LP_ERR_ARG, "pivot out of range");
 		CU(cudaSetDevice(opt.device));
 		k_book1<T><<<grid, NT, 0, stream>>>(d, p, q);
@@ -362,11 +403,74 @@ public:
 		return B200LP_OK;
 	}
 
+	int shard_columns(int64_t* col0, int64_t* ncols) override {
+		const long long nsg = d.n - d.m;      // with the identity slack block recognised
+		if (col0) *col0 = nsg * rank / nranks;
+		if (ncols) *ncols = nsg * (rank + 1) / nranks - nsg * rank / nranks;
+		return B200LP_OK;
+	}
+
+	int shard_rows(int64_t* row0, int64_t* rows) override {
+		if (row0) *row0 = d.row0;
+		if (rows) *rows = std::max<long long>(0, std::min<long long>(d.m, d.row0 + d.ldb) - d.row0);
+		return B200LP_OK;
+	}
+
 	int64_t bytes_per_pivot() const override {
 		return (int64_t)sizeof(T) * (2 * d.m * d.m + d.m * (d.n - d.m));
 	}
 
+	// ---- sharded mode: peer mapping of the A shards and mailboxes (CUDA IPC over NVLink) ----
+
+	int ipc_export(void* out) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "ipc_export before upload/generate (the A shard is allocated there)");
+		CU(cudaSetDevice(opt.device));
+		cudaIpcMemHandle_t h[2];
+		CU(cudaIpcGetMemHandle(&h[0], (void*)hA));
+		CU(cudaIpcGetMemHandle(&h[1], (void*)mbox));
+		std::memcpy(out, h, sizeof(h));
+		return B200LP_OK;
+	}
+
+	int ipc_import(const void* all, int n) override {
+		if (n != nranks) return fail(B200LP_ERR_ARG, "ipc_import: handle count differs from the engine's rank count");
+		if (!have_data) return fail(B200LP_ERR_STATE, "ipc_import before upload/generate");
+		CU(cudaSetDevice(opt.device));
+		const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all);
+		for (int r = 0; r < nranks; ++r) {
+			if (r == rank) { d.A_peer[r] = hA; d.mbox_peer[r] = mbox; continue; }
+			void *pa = nullptr, *pm = nullptr;
+			CU(cudaIpcOpenMemHandle(&pa, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
+			CU(cudaIpcOpenMemHandle(&pm, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+			opened.push_back(pa);
+			opened.push_back(pm);
+			d.A_peer[r] = static_cast<const T*>(pa);
+			d.mbox_peer[r] = static_cast<unsigned char*>(pm);
+		}
+		peers_mapped = true;
+		return B200LP_OK;
+	}
+
 private:
+	// (re)allocate the local A shard for `ns_new` global dense columns
+	cudaError_t set_columns(long long ns_new) {
+		for (int r = 0; r <= nranks; ++r) d.colstart[r] = ns_new * r / nranks;
+		const long long nsl_new = d.colstart[rank + 1] - d.colstart[rank];
+		if (!hA || nsl_new != d.nsl) {
+			if (hA) cudaFree(hA);
+			hA = nullptr;
+			cudaError_t e = cudaMalloc((void**)&hA, std::max<size_t>(1, (size_t)d.ld * nsl_new) * sizeof(T));
+			if (e != cudaSuccess) return e;
+		}
+		d.A = hA;
+		d.A_peer[rank] = hA;
+		d.ns = ns_new;
+		d.nsl = nsl_new;
+		d.col0 = d.colstart[rank];
+		ns = ns_new;
+		return cudaSuccess;
+	}
+
 	template <typename U>
 	cudaError_t alloc(U** p, size_t count) {
 		cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(U));
@@ -376,6 +480,8 @@ private:
 
 	void release() {
 		if (stream) cudaStreamSynchronize(stream);
+		for (void* p : opened) cudaIpcCloseMemHandle(p);
+		opened.clear();
 		for (void* p : owned) cudaFree(p);
 		if (hA) cudaFree(hA);
 		owned.clear();
@@ -432,7 +538,7 @@ private:
 
 	void launch_update_ftran(bool update, bool ftran, long long p) {
 		const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
-		const long long tiles = (d.ld + tr - 1) / tr * d.nchunk;
+		const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
 		const int g = (int)std::max<long long>(1, std::min<long long>(tiles, grid));
 #define LAUNCH_UF(WC_)                                                                                    \
 		do {                                                                                              \
@@ -479,9 +585,11 @@ private:
 	T* hA = nullptr;           // mutable aliases of the const members of d
 	T* hb = nullptr;
 	T* hcst = nullptr;
-	T* spare = nullptr;
+	unsigned char* mbox = nullptr;
+	size_t mbox_bytes = 0;
 	void* pinned = nullptr;
-	std::vector<void*> owned;
+	std::vector<void*> owned, opened;
+	bool peers_mapped = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	int num_sms = 0, max_grid = 0, wc = 1;
 	bool have_data = false, in_flight = false;
@@ -489,9 +597,10 @@ private:
 };
 
 template <typename T>
-int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out) {
+int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out, int rank = 0, int nranks = 1) {
 	if (!out) return fail(B200LP_ERR_ARG, "out is NULL");
 	*out = nullptr;
+	if (nranks < 1 || nranks > MAXR || rank < 0 || rank >= nranks) return fail(B200LP_ERR_ARG, "need 0 <= rank < nranks <= 8");
 	if (m <= 0 || n <= 0 || m > n) return fail(B200LP_ERR_ARG, "need 0 < m <= n (v4:402)");
 	if (n >= ((int64_t)1 << 31)) return fail(B200LP_ERR_ARG, "n must fit a 32-bit basis index");
 	b200lp_options o;
@@ -502,7 +611,7 @@ int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine
 		return fail(B200LP_ERR_NO_GPU, "no CUDA device: the engine has no CPU fallback");
 	}
 	if (o.device < 0 || o.device >= ndev) return fail(B200LP_ERR_ARG, "device ordinal out of range");
-	auto* e = new Engine<T>(m, n, o);
+	auto* e = new Engine<T>(m, n, o, rank, nranks);
 	int rc = e->init();
 	if (rc) { delete e; return rc; }
 	*out = e;
@@ -545,9 +654,40 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 
 } // namespace
 
+// host-side twin of k_generate_dense (same counter-based numbers), threaded over columns
+template <typename T>
+static void lpgen_host(T* A, T* b, T* c, int64_t m, int64_t n, int64_t col0, int64_t ncols, uint64_t seed) {
+	const int64_t ns = n - m;
+	if (A && ncols > 0) {
+		const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), ncols));
+		auto work = [&](int64_t j0, int64_t j1) {
+			for (int64_t jj = j0; jj < j1; ++jj) {
+				const int64_t j = col0 + jj;
+				T* col = A + (size_t)jj * m;
+				if (j < ns) for (int64_t i = 0; i < m; ++i) col[i] = (T)u01(seed, 0, (uint64_t)(i * ns + j));
+				else        for (int64_t i = 0; i < m; ++i) col[i] = (T)(i == j - ns);
+			}
+		};
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, ncols * t / nt, ncols * (t + 1) / nt);
+		for (auto& t : th) t.join();
+	}
+	if (b) for (int64_t i = 0; i < m; ++i) b[i] = (T)(0.5 * (double)ns * (1.0 + u01(seed, 1, (uint64_t)i)));
+	if (c) for (int64_t j = 0; j < n; ++j) c[j] = j < ns ? (T)(0.5 + u01(seed, 2, (uint64_t)j)) : T(0);
+}
+
 // ------------------------------------------------------------------ C ABI
 
 extern "C" {
+
+int b200lp_lpgen_dense_host(int32_t dtype, void* A_cols, void* b, void* c, int64_t m, int64_t n,
+		int64_t col0, int64_t ncols, uint64_t seed) {
+	if (m <= 0 || n < m || col0 < 0 || ncols < 0 || col0 + ncols > n) return fail(B200LP_ERR_ARG, "lpgen: bad shape");
+	if (dtype == B200LP_F64) lpgen_host<double>((double*)A_cols, (double*)b, (double*)c, m, n, col0, ncols, seed);
+	else if (dtype == B200LP_F32) lpgen_host<float>((float*)A_cols, (float*)b, (float*)c, m, n, col0, ncols, seed);
+	else return fail(B200LP_ERR_ARG, "dtype must be B200LP_F32 or B200LP_F64");
+	return B200LP_OK;
+}
 
 void b200lp_default_options(b200lp_options* opt) {
 	if (!opt) return;
@@ -574,7 +714,25 @@ int b200lp_create(int32_t dtype, int64_t m, int64_t n, const b200lp_options* opt
 	return fail(B200LP_ERR_ARG, "dtype must be B200LP_F32 or B200LP_F64");
 }
 
+int b200lp_create_sharded(int32_t dtype, int64_t m, int64_t n, int32_t rank, int32_t nranks, const b200lp_options* opt,
+		b200lp_engine** out) {
+	if (dtype == B200LP_F64) return create_engine<double>(m, n, opt, out, rank, nranks);
+	if (dtype == B200LP_F32) return create_engine<float>(m, n, opt, out, rank, nranks);
+	return fail(B200LP_ERR_ARG, "dtype must be B200LP_F32 or B200LP_F64");
+}
+
 #define NEED(e) do { if (!(e)) return fail(B200LP_ERR_ARG, "engine is NULL"); } while (0)
+
+int b200lp_ipc_handle_bytes(void) { return (int)(2 * sizeof(cudaIpcMemHandle_t)); }
+int b200lp_ipc_export(b200lp_engine* e, void* out) { NEED(e); if (!out) return fail(B200LP_ERR_ARG, "out is NULL"); return e->ipc_export(out); }
+int b200lp_ipc_import(b200lp_engine* e, const void* all, int32_t nranks) { NEED(e); if (!all) return fail(B200LP_ERR_ARG, "handles are NULL"); return e->ipc_import(all, nranks); }
+int b200lp_shard_rows(b200lp_engine* e, int64_t* row0, int64_t* rows) { NEED(e); return e->shard_rows(row0, rows); }
+int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols) { NEED(e); return e->shard_columns(col0, ncols); }
+int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int64_t ncols, const void* b, const void* c) {
+	NEED(e);
+	if (!Acols || !b || !c) return fail(B200LP_ERR_ARG, "Acols, b, c must not be NULL");
+	return e->upload_columns(Acols, col0, ncols, b, c);
+}
 
 int b200lp_destroy(b200lp_engine* e) { delete e; return B200LP_OK; }
 int b200lp_upload(b200lp_engine* e, const void* A, const void* b, const void* c) {

@@ -43,6 +43,7 @@ constexpr int SUBW = 32;      // FTRAN sub-block (columns)
 constexpr int SLICE = 256;    // O(m) dot slice (elements)
 constexpr int PRICE_NC = 4;   // columns priced together by one CTA
 constexpr int MIN_CTAS = 2;   // resident CTAs per SM the persistent kernel is compiled for
+constexpr int MAXR = 8;       // ranks (GPUs) of one NVSwitch box
 
 template <typename T> struct VecT;
 template <> struct VecT<double> { using V = double2; static constexpr int N = 2; };
@@ -63,7 +64,8 @@ struct Ctl {
 	int status;               // B200LP_STATUS_*
 	int pending;              // rank-1 update (E_q, row_q) not yet applied to B^-1
 	int done;                 // optimum / unbounded reached
-	int bad;                  // slack-block check failed
+	int bad;                  // peer barrier timed out (sharded mode)
+	unsigned long long xepoch; // cross-GPU barrier epoch, monotonic over the engine's life
 	long long p, q;           // last entering column / leaving row
 	double min_e;             // last pricing minimum
 	double c_b_q;             // c_b[q] before the swap (v4:339)
@@ -88,7 +90,27 @@ struct Dev {
 	int2* trace;
 	long long trace_cap;
 	double eps;
+	// ---- sharding over the GPUs of one box (single GPU: rank 0 of 1, row0 = 0, ldb = ld, col0 = 0, nsl = ns)
+	// B^-1 is row-block sharded (B holds rows [row0, row0+ldb) with leading dimension ldb),
+	// A is column-block sharded (A holds dense columns [col0, col0+nsl), ld rows each),
+	// every O(m) vector is replicated.
+	int rank, nranks;
+	long long row0, ldb;
+	long long col0, nsl;
+	long long k0, k1;                 // share of the unit (slack) columns priced on this rank
+	long long colstart[MAXR + 1], rowstart[MAXR + 1];
+	const T* A_peer[MAXR];            // every rank's A shard (peer-mapped over NVLink)
+	unsigned char* mbox_peer[MAXR];   // every rank's mailbox: [XHdr][alpha ld][row_q ld]; alpha/row_q above point into our own
+	T* acol;                          // local copy of the entering column (sharded mode only)
 };
+
+// head of a rank's mailbox; peers store into it over NVLink
+struct XHdr {
+	unsigned long long xflag[MAXR];   // xflag[r] = last barrier epoch rank r has signalled to us
+	Cand candx[MAXR];                 // candx[r] = rank r's pricing candidate
+	unsigned long long pad[8];
+};
+static_assert(sizeof(XHdr) % 256 == 0, "mailbox vectors must stay 16-byte aligned");
 
 // ---------------------------------------------------------------- memory ops
 
@@ -232,7 +254,7 @@ __device__ __forceinline__ long long reduce_counts(const long long* cnt, int n, 
 // range), e_j = y_k - c_j for the unit columns, fused with the argmin.
 // Replaces cublasSgemm(M=1) + cub::DeviceReduce::ArgMin (v4:289-294).
 template <typename T>
-__device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts, long long idx_base) {
+__device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
@@ -242,7 +264,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts, lon
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 
-	const long long c0 = d.ns * part / nparts, c1 = d.ns * (part + 1) / nparts;
+	const long long c0 = d.nsl * part / nparts, c1 = d.nsl * (part + 1) / nparts;   // local columns
 	int buf = 0;
 	for (long long col = c0; col < c1; col += PRICE_NC, buf ^= 1) {
 		const T* ap[PRICE_NC];
@@ -281,18 +303,17 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts, lon
 			T s = (T)sh.wsum[buf][tid][0];
 #pragma unroll
 			for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
-			const double e = (double)(s - d.c[col + tid]);
-			const long long j = idx_base + col + tid;
+			const long long j = d.col0 + col + tid;     // global column index
+			const double e = (double)(s - d.c[j]);
 			if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
 		}
 	}
 
 	// unit (slack) columns: e_j = y_k - c_j, no matrix bytes (the reference reads
 	// the identity block through the same GEMM; 0*y terms vanish exactly)
-	const long long nu = d.n - d.ns;
-	for (long long k = (long long)part * NT + tid; k < nu; k += (long long)nparts * NT) {
+	for (long long k = d.k0 + (long long)part * NT + tid; k < d.k1; k += (long long)nparts * NT) {
 		const double e = (double)(d.y[k] - d.c[d.ns + k]);
-		const long long j = idx_base + d.ns + k;
+		const long long j = d.ns + k;
 		if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
 	}
 
@@ -309,7 +330,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts, lon
 // WR*32*VN rows x CHUNK columns.  row_q[chunk] and a_p[chunk] are staged in
 // shared memory.  alpha_part[chunk][row] receives the chunk partial.
 template <typename T, int WC, bool UPDATE, bool FTRAN>
-__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, long long p, int part, int nparts) {
+__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, long long uk, int part, int nparts) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
@@ -321,14 +342,12 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, long long p, int p
 	static_assert(NT == CHUNK, "staging assumes one thread per chunk column");
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int wr = warp % WR, wc = warp / WR;
-	const long long ld = d.ld, m = d.m;
+	const long long ld = d.ldb, m = d.m;   // local row block
 	const long long ntr = (ld + TR - 1) / TR;
 	const long long ntiles = ntr * d.nchunk;
 	T* stage_rq = reinterpret_cast<T*>(sh.stage[0]);
 	T* stage_a = reinterpret_cast<T*>(sh.stage[1]);
-	const bool unit = p >= d.ns;
-	const T* acol = unit ? nullptr : d.A + p * ld;
-	const long long uk = p - d.ns;
+	const bool unit = acol == nullptr;     // entering column is the unit vector e_uk
 
 	for (long long tile = part; tile < ntiles; tile += nparts) {
 		const long long rt = tile % ntr, ck = tile / ntr;
@@ -339,7 +358,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, long long p, int p
 			T r = T(0), a = T(0);
 			if (j < m) {
 				if (UPDATE) r = d.row_q[j];
-				if (FTRAN) a = unit ? (j == uk ? T(1) : T(0)) : __ldg(acol + j);
+				if (FTRAN) a = unit ? (j == uk ? T(1) : T(0)) : acol[j];   // plain load: acol may have been written by this kernel
 			}
 			stage_rq[tid] = r;
 			stage_a[tid] = a;
@@ -354,7 +373,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, long long p, int p
 
 		if (active) {
 			V Ev;
-			if (UPDATE) Ev = *reinterpret_cast<const V*>(d.E_q + row);
+			if (UPDATE) Ev = *reinterpret_cast<const V*>(d.E_q + d.row0 + row);
 			// pairwise tree over this warp's sub-blocks, kept as a binary-counter stack so
 			// at most log2(SUBS)+1 partials are live
 			T stk[4][VN];
@@ -452,21 +471,26 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, long long p, int p
 // alpha_i = sum of the chunk partials (left to right); theta_i = x_b_i/alpha_i
 // over alpha_i > 0 (strict, v4:203); masked argmin + eligible-row count.
 // Replaces cudaMemset + compute_theta + D2H + cub ArgMin (v4:311-325).
-template <typename T>
-__device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts, long long row_base) {
+template <typename T, bool FROM_PARTIALS>
+__device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 	const int tid = threadIdx.x;
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 	long long elig = 0;
 	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
-		T a = __ldcg(d.alpha_part + i);
+		T a;
+		if (FROM_PARTIALS) {
+			a = __ldcg(d.alpha_part + i);
 #pragma unroll 8
-		for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ld + i);
-		d.alpha[i] = a;
+			for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ldb + i);
+			d.alpha[i] = a;
+		} else {
+			a = d.alpha[i];   // already exchanged between the ranks
+		}
 		if (a > T(0)) {
 			++elig;
 			const double th = (double)(d.x_b[i] / a);
-			if (cand_better(th, row_base + i, best_v, best_i)) { best_v = th; best_i = row_base + i; }
+			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
 	}
 	block_argmin(best_v, best_i, sh);
@@ -500,7 +524,7 @@ __device__ void book1_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 		const long long i = s * SLICE + tid;
 		T t1 = T(0), t2 = T(0);
 		if (i < d.m) {
-			const T rq = d.B[q + i * d.ld];
+			const T rq = d.B[q + i * d.ldb];
 			const T eq = (i != q) ? (-d.alpha[i] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
 			d.row_q[i] = rq;
 			d.E_q[i] = eq;
@@ -588,19 +612,20 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 
 	while (it < it_end) {
 		// ---- pricing + entering column (v4:288-302)
-		price_phase<T>(d, sh, me, G, 0);
+		price_phase<T>(d, sh, me, G);
 		grid_barrier(ctl, epoch);
 		reduce_cands(d.cand, G, min_e, p, sh);
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
 		// ---- pending rank-1 update fused with the FTRAN of column p
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, p, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, p, me, G);
+		const T* acol = p < d.ns ? d.A + p * d.ld : nullptr;
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, acol, p - d.ns, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, acol, p - d.ns, me, G);
 		pending = 0;
 		grid_barrier(ctl, epoch);
 
 		// ---- ratio test (v4:311-325)
-		ratio_phase<T>(d, sh, me, G, 0);
+		ratio_phase<T, true>(d, sh, me, G);
 		grid_barrier(ctl, epoch);
 		double th;
 		reduce_cands(d.cand, G, th, q, sh);
@@ -628,6 +653,249 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	}
 }
 
+// ---------------------------------------------------------------- sharded (multi-GPU) loop
+//
+// One process per GPU, the same persistent kernel on every rank.  B^-1 is row-block
+// sharded, A column-block sharded, every O(m) vector (y, x_b, c_b, alpha, E_q, row_q,
+// b_ixs) is replicated, so all ranks take identical decisions and the per-row / per-column
+// sums are exactly the single-GPU ones (results are bit-identical for every GPU count).
+// Three exchanges per pivot, all direct peer stores over NVLink into the receivers'
+// mailboxes followed by a flag barrier — no NCCL call and no host on the data path:
+//   X1  pricing candidate (value, index), 16 B per rank            (replaces the global cub ArgMin)
+//   X2  alpha slices of the local row block, m/R values per rank   (after the fused update+FTRAN)
+//   X3  row q of B^-1 from its owner, m values                     (replaces cublasScopy, v4:331)
+// The entering column a_p is pulled from its owner's A shard with peer loads.
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+// grid barrier whose release/acquire fences are system scope (peer stores must be
+// visible to the other GPUs before the flag that announces them)
+__device__ __forceinline__ void grid_barrier_sys(Ctl* ctl, unsigned long long& epoch) {
+	epoch += gridDim.x;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		if (gridDim.x > 1) {
+			atomicAdd(&ctl->bar, 1ULL);
+			while (*((volatile unsigned long long*)&ctl->bar) < epoch) { }
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+}
+
+// cross-GPU flag barrier, executed by CTA 0 between two grid_barrier_sys calls:
+// thread r signals rank r (store into ITS mailbox) and waits for rank r's signal in ours.
+template <typename T>
+__device__ __forceinline__ void xsync(const Dev<T>& d, unsigned long long xepoch) {
+	if (blockIdx.x != 0) return;
+	if (threadIdx.x < d.nranks) {
+		const int r = threadIdx.x;
+		__threadfence_system();
+		st_release_sys(&reinterpret_cast<XHdr*>(d.mbox_peer[r])->xflag[d.rank], xepoch);
+		const unsigned long long* mine = &reinterpret_cast<XHdr*>(d.mbox_peer[d.rank])->xflag[r];
+		const unsigned long long t0 = globaltimer_ns();
+		while (ld_acquire_sys(mine) < xepoch) {
+			if (globaltimer_ns() - t0 > 20000000000ULL) { d.ctl->bad = 1; break; }   // 20 s: a peer died
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+}
+
+// full exchange step: everything stored to peers before it is visible to them after it
+template <typename T>
+__device__ __forceinline__ void xbarrier(const Dev<T>& d, unsigned long long& epoch, unsigned long long& xepoch) {
+	grid_barrier_sys(d.ctl, epoch);
+	xsync(d, ++xepoch);
+	grid_barrier_sys(d.ctl, epoch);
+}
+
+// X1: CTA 0 reduces this rank's per-CTA candidates and stores the winner into every mailbox
+template <typename T>
+__device__ void push_price_candidate(const Dev<T>& d, Smem& sh) {
+	if (blockIdx.x != 0) return;
+	double v; long long i;
+	reduce_cands(d.cand, gridDim.x, v, i, sh);
+	if (threadIdx.x < d.nranks) {
+		Cand* dst = &reinterpret_cast<XHdr*>(d.mbox_peer[threadIdx.x])->candx[d.rank];
+		dst->val = v;
+		dst->idx = i;
+	}
+}
+
+// pull the entering column from its owner's A shard into the local staging vector
+template <typename T>
+__device__ void fetch_column(const Dev<T>& d, long long p, int part, int nparts) {
+	using M = Mem<T>;
+	using V = typename VecT<T>::V;
+	constexpr int VN = VecT<T>::N;
+	int o = 0;
+	while (o + 1 < d.nranks && p >= d.colstart[o + 1]) ++o;
+	const T* src = d.A_peer[o] + (p - d.colstart[o]) * d.ld;
+	for (long long i = ((long long)part * NT + threadIdx.x) * VN; i < d.ld; i += (long long)nparts * NT * VN)
+		*reinterpret_cast<V*>(d.acol + i) = M::ld_nc(src + i);
+}
+
+// X2: alpha of the local rows = sum of the chunk partials (left to right), stored into every rank's alpha
+template <typename T>
+__device__ void push_alpha_phase(const Dev<T>& d, int part, int nparts) {
+	const long long nloc = d.ldb;
+	for (long long i = (long long)part * NT + threadIdx.x; i < nloc; i += (long long)nparts * NT) {
+		T a = __ldcg(d.alpha_part + i);
+#pragma unroll 8
+		for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ldb + i);
+		for (int r = 0; r < d.nranks; ++r)
+			reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr))[d.row0 + i] = a;
+	}
+}
+
+// book1, sharded: E_q and the c_b.E_q slice partials on every rank (replicated data);
+// X3: the owner of row q gathers it from its B^-1 block and stores it into every rank's row_q.
+template <typename T>
+__device__ void book1a_sharded(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const T alpha_q = d.alpha[q];
+	const T c_p = d.c[p];
+	const bool owner = q >= d.row0 && q < d.row0 + d.ldb;
+	for (long long s = part; s < d.nslice; s += nparts) {
+		const long long i = s * SLICE + tid;
+		T t2 = T(0);
+		if (i < d.m) {
+			const T eq = (i != q) ? (-d.alpha[i] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			d.E_q[i] = eq;
+			T cb = d.c_b[i];
+			if (i == q) { d.ctl->c_b_q = (double)cb; cb = c_p; }
+			t2 = fma_t(cb, eq, T(0));
+			if (owner) {
+				const T rq = d.B[(q - d.row0) + i * d.ldb];
+				for (int r = 0; r < d.nranks; ++r)
+					(reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr)) + d.ld)[i] = rq;
+			}
+		}
+		t2 = warp_butterfly_sum(t2);
+		__syncthreads();
+		if (lane == 0) sh.dsum[1][warp] = (double)t2;
+		__syncthreads();
+		if (tid == 0) {
+			T a = T(0);
+#pragma unroll
+			for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[1][w];
+			d.dpart[(long long)d.nslice + s] = a;
+		}
+	}
+}
+
+// row_q.b slice partials once row_q has arrived
+template <typename T>
+__device__ void book1b_sharded(const Dev<T>& d, Smem& sh, int part, int nparts) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (long long s = part; s < d.nslice; s += nparts) {
+		const long long i = s * SLICE + tid;
+		T t1 = i < d.m ? fma_t(d.row_q[i], d.b[i], T(0)) : T(0);
+		t1 = warp_butterfly_sum(t1);
+		__syncthreads();
+		if (lane == 0) sh.dsum[0][warp] = (double)t1;
+		__syncthreads();
+		if (tid == 0) {
+			T a = T(0);
+#pragma unroll
+			for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[0][w];
+			d.dpart[s] = a;
+		}
+	}
+}
+
+template <typename T, int WC>
+__global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T> d) {
+	__shared__ Smem sh;
+	Ctl* ctl = d.ctl;
+	const int G = gridDim.x, me = blockIdx.x;
+	unsigned long long epoch = 0;
+	unsigned long long xepoch = ctl->xepoch;
+
+	long long it = ctl->iter, pivots = ctl->pivots;
+	const long long it_end = ctl->it_end;
+	int pending = ctl->pending;
+	int status = 0, done = 0, bad = 0;
+	long long p = ctl->p, q = ctl->q;
+	double min_e = ctl->min_e;
+	const XHdr* mine = reinterpret_cast<const XHdr*>(d.mbox_peer[d.rank]);
+
+	while (it < it_end) {
+		// ---- pricing over the local column block, X1
+		price_phase<T>(d, sh, me, G);
+		grid_barrier_sys(ctl, epoch);
+		push_price_candidate<T>(d, sh);
+		xbarrier(d, epoch, xepoch);
+		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
+		min_e = CUDART_INF; p = LLONG_MAX;
+		for (int r = 0; r < d.nranks; ++r) {       // same fixed order on every rank and CTA
+			const double cv = __ldcg(&mine->candx[r].val);
+			const long long ci = __ldcg(&mine->candx[r].idx);
+			if (cand_better(cv, ci, min_e, p)) { min_e = cv; p = ci; }
+		}
+		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
+
+		// ---- entering column from its owner, then the fused update + FTRAN on the local rows
+		const bool dense = p < d.ns;
+		if (dense) {
+			fetch_column<T>(d, p, me, G);
+			grid_barrier(ctl, epoch);
+		}
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, me, G);
+		pending = 0;
+		grid_barrier(ctl, epoch);
+
+		// ---- X2: alpha slices to every rank, then the ratio test on the full alpha (replicated)
+		push_alpha_phase<T>(d, me, G);
+		xbarrier(d, epoch, xepoch);
+		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
+		ratio_phase<T, false>(d, sh, me, G);
+		grid_barrier(ctl, epoch);
+		double th;
+		reduce_cands(d.cand, G, th, q, sh);
+		const long long elig = reduce_counts(d.cnt, G, sh);
+		if (elig == 0) { status = 2; done = 1; ++it; break; }
+
+		// ---- pivot: E_q everywhere, X3 row q from its owner, then the replicated O(m) updates
+		book1a_sharded<T>(d, sh, p, q, me, G);
+		xbarrier(d, epoch, xepoch);
+		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
+		book1b_sharded<T>(d, sh, me, G);
+		grid_barrier(ctl, epoch);
+		book2_phase<T>(d, sh, p, q, me, G);
+		if (me == 0 && threadIdx.x == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
+		pending = 1;
+		++pivots;
+		++it;
+		grid_barrier(ctl, epoch);
+	}
+
+	if (me == 0) {
+		const double z = objective<T>(d, sh);
+		if (threadIdx.x == 0) {
+			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
+			ctl->status = status; ctl->done = done; ctl->xepoch = xepoch;
+			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
+			if (bad) ctl->bad = 1;
+		}
+	}
+}
+
 // ---------------------------------------------------------------- stand-alone phase kernels
 // (unit tests, one-launch-per-phase mode, sharded driver).  p / q are passed by
 // the host or read from ctl by the caller.
@@ -635,7 +903,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 template <typename T>
 __global__ void __launch_bounds__(NT) k_price(Dev<T> d) {
 	__shared__ Smem sh;
-	price_phase<T>(d, sh, blockIdx.x, gridDim.x, 0);
+	price_phase<T>(d, sh, blockIdx.x, gridDim.x);
 }
 
 // final argmin over the per-CTA candidates -> ctl->p / ctl->min_e (kind 0) or ctl->q + eligible (kind 1)
@@ -655,13 +923,13 @@ __global__ void __launch_bounds__(NT) k_pick(Dev<T> d, int ncand, int kind) {
 template <typename T, int WC, bool UPDATE, bool FTRAN>
 __global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p) {
 	__shared__ Smem sh;
-	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, p, blockIdx.x, gridDim.x);
+	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, blockIdx.x, gridDim.x);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(NT) k_ratio(Dev<T> d) {
 	__shared__ Smem sh;
-	ratio_phase<T>(d, sh, blockIdx.x, gridDim.x, 0);
+	ratio_phase<T, true>(d, sh, blockIdx.x, gridDim.x);
 }
 
 template <typename T>
@@ -689,10 +957,10 @@ __global__ void __launch_bounds__(NT) k_objective(Dev<T> d) {
 // b_ixs[j] = n-m+j, y = c_b; padding rows zero.
 template <typename T>
 __global__ void k_reset(Dev<T> d) {
-	const long long tot = d.ld * d.m;
+	const long long tot = d.ldb * d.m;
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += stride) {
-		const long long i = e % d.ld, j = e / d.ld;
+		const long long i = d.row0 + e % d.ldb, j = e / d.ldb;
 		d.B[e] = (i == j) ? T(1) : T(0);
 	}
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.ld; i += stride) {
@@ -722,12 +990,13 @@ __host__ __device__ __forceinline__ double u01(uint64_t seed, uint64_t stream, u
 // dense synthetic LP (same numbers as oracle/lpgen_dense_*): A_s ~ U(0,1),
 // b = (ns/2) U(1,2), c_s ~ U(0.5,1.5), slack costs 0
 template <typename T>
-__global__ void k_generate_dense(T* A, T* b, T* c, long long m, long long n, long long ns, long long ld, uint64_t seed) {
+__global__ void k_generate_dense(T* A, T* b, T* c, long long m, long long n, long long ns, long long ld, uint64_t seed,
+		long long col0, long long nsl) {
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long tot = ld * ns;
+	const long long tot = ld * nsl;           // this rank's column block [col0, col0 + nsl)
 	for (long long e = g; e < tot; e += stride) {
-		const long long i = e % ld, j = e / ld;
+		const long long i = e % ld, j = col0 + e / ld;
 		A[e] = i < m ? (T)u01(seed, 0, (uint64_t)(i * ns + j)) : T(0);
 	}
 	for (long long i = g; i < ld; i += stride) b[i] = i < m ? (T)(0.5 * (double)ns * (1.0 + u01(seed, 1, (uint64_t)i))) : T(0);

@@ -221,6 +221,22 @@ class Engine:
         return self._L.b200lp_bytes_per_pivot(self._h)
 
 
+def lpgen_dense_into(A_ptr, b_ptr, c_ptr, m, n, col0, ncols, seed, dtype=np.float64):
+    """Fill caller-owned host memory (e.g. pinned) with columns [col0, col0+ncols) of the synthetic dense LP."""
+    vp = lambda p: C.c_void_p(int(p)) if p else None
+    capi.check(capi.lib().b200lp_lpgen_dense_host(_dtype_code(dtype), vp(A_ptr), vp(b_ptr), vp(c_ptr), m, n, col0, ncols, seed))
+
+
+def lpgen_dense(m, n, seed=1, dtype=np.float64):
+    """Synthetic dense LP of the benchmark configurations (full [A_s, I] matrix, column-major)."""
+    dt = np.dtype(dtype)
+    A = np.empty((m, n), dt, order="F")
+    b = np.empty(m, dt)
+    c = np.empty(n, dt)
+    lpgen_dense_into(A.ctypes.data, b.ctypes.data, c.ctypes.data, m, n, 0, n, seed, dt)
+    return A, b, c
+
+
 # ---------------------------------------------------------------- text format + printing
 
 def read_lp(path_or_file, dtype=REAL):
