@@ -60,7 +60,8 @@ typedef struct {
 	int32_t check_slack;  /* 1: verify that the last m columns are the identity (default);
 	                         0: trust the caller like the reference does (v4:272) */
 	int32_t mode;         /* 0 = persistent cooperative kernel, 1 = one launch per phase */
-	int32_t reserved;
+	int32_t profile;      /* > 0: record phase time stamps for the first `profile` iterations of every
+	                         persistent launch (b200lp_download_profile); 0 = off (default) */
 } b200lp_options;
 
 typedef struct {
@@ -157,6 +158,14 @@ int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols); /* st
  * the caller vouches for the identity slack block, which is never transferred */
 int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int64_t ncols,
 		const void* b, const void* c);
+
+/* ---- in-kernel phase profile (options.profile > 0) ----
+ * CTA 0 of the persistent kernel stamps %globaltimer (ns) at every phase boundary; one record of
+ * b200lp_profile_stamps() values per iteration of the LAST launch (0 = point not reached).
+ * Replaces the reference's unsynchronised host chrono timers (v4:293-297, 330-357, 456-471). */
+int b200lp_profile_stamps(void);
+const char* b200lp_profile_names(void);   /* JSON: interval names of the single-GPU and the sharded loop */
+int b200lp_download_profile(b200lp_engine* e, uint64_t* out, int64_t cap_iters, int64_t* n_iters);
 
 /* ---- synthetic input (bench / tests) ----
  * Host-side twin of b200lp_generate_dense: columns [col0, col0 + ncols) of the full

@@ -17,6 +17,8 @@
 #      (v4:289-290, 307-308, 333 pass host stack addresses)
 #   P6 pivot-trace hook after the q read-back (v4:325), iteration count export,
 #      "# Iteration" printing silenced (v4:287)
+#   P7 64-bit sizes and element offsets (v4:33, 60, 77, 86, 246, 248, 269, 308): the shipped
+#      `int` products m*n, (m+1)*n and p*m overflow at m = 32768, n = 65536 (config C4)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${REFERENCE_DIR:-/root/reference}"
@@ -39,6 +41,14 @@ $NVCC --std=c++20 $ARCH "$SRC" -o "$OUT/v4_stock.out" -ccbin "$CCBIN" -lcublas
 patch_src() { # $1 = S|D  $2 = out file
 	sed -E \
 		-e '18s/constexpr real EPS/static real EPS/' \
+		-e '33s/int size;/long long size;/' \
+		-e '60s/constexpr int R2C\(int i, int j, int m\)/constexpr long long R2C(long long i, long long j, long long m)/' \
+		-e '77s/int n, const char/size_t n, const char/' \
+		-e '86s/int size, cudaMemcpyKind/size_t size, cudaMemcpyKind/' \
+		-e '246s/\{d_A, m \* n\}/{d_A, (long long)m * n}/; 246s/\{d_B_inv, m \* m\}/{d_B_inv, (long long)m * m}/' \
+		-e '248s/\{d_D, \(m \+ 1\) \* n\}/{d_D, (long long)(m + 1) * n}/' \
+		-e '269s/A, m \* n,/A, (long long)m * n,/' \
+		-e '308s/d_A \+ p \* m/d_A + (long long)p * m/' \
 		-e '19s/constexpr int MAX_ITER/static int MAX_ITER/' \
 		-e '243s/$/ real *d_one, *d_zero; cudaMalloc(\&d_one, sizeof(real)); cudaMalloc(\&d_zero, sizeof(real)); cudaMemcpy(d_one, \&one, sizeof(real), cudaMemcpyHostToDevice); cudaMemcpy(d_zero, \&zero, sizeof(real), cudaMemcpyHostToDevice);/' \
 		-e '272s/dim3\(blocks_for_m, blocks_for_m\)/dim3((m + BS_2D - 1) \/ BS_2D, (m + BS_2D - 1) \/ BS_2D)/' \
@@ -59,7 +69,8 @@ patch_src() { # $1 = S|D  $2 = out file
 	grep -q 'static real EPS' "$2" && grep -q 'static int MAX_ITER' "$2" && grep -q 'd_one, d_y_aug' "$2" \
 		&& grep -q 'ref_trace\[2 \* i\]' "$2" && grep -q 'ref_iterations =' "$2" \
 		&& grep -q 'if (!ref_quiet)' "$2" && grep -q 'd_c_b, m, cudaMemcpyDeviceToDevice' "$2" \
-		&& [ "$(grep -c 'BS_2D - 1' "$2")" = "2" ] || { echo "make_ref: patch did not apply cleanly" >&2; exit 1; }
+		&& [ "$(grep -c 'BS_2D - 1' "$2")" = "2" ] && [ "$(grep -c '(long long)' "$2")" -ge 4 ] \
+		&& grep -q 'long long R2C' "$2" && grep -q 'long long size;' "$2" || { echo "make_ref: patch did not apply cleanly" >&2; exit 1; }
 }
 
 for V in D S; do

@@ -21,12 +21,13 @@ EXPORTS = [
     "b200lp_last_error", "b200lp_version",
     "b200lp_create_sharded", "b200lp_ipc_handle_bytes", "b200lp_ipc_export", "b200lp_ipc_import", "b200lp_shard_rows",
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
+    "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile",
 ]
 
 
 class Options(C.Structure):
     _fields_ = [("eps", C.c_double), ("max_iter", C.c_int64), ("device", C.c_int32), ("grid_ctas", C.c_int32),
-                ("tile_shape", C.c_int32), ("check_slack", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32)]
+                ("tile_shape", C.c_int32), ("check_slack", C.c_int32), ("mode", C.c_int32), ("profile", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -86,6 +87,9 @@ def lib() -> C.CDLL:
         "b200lp_shard_columns": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "b200lp_upload_columns": (C.c_int, [vp, vp, i64, i64, vp, vp]),
         "b200lp_lpgen_dense_host": (C.c_int, [i32, vp, vp, vp, i64, i64, i64, i64, C.c_uint64]),
+        "b200lp_profile_stamps": (C.c_int, []),
+        "b200lp_profile_names": (C.c_char_p, []),
+        "b200lp_download_profile": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
         "b200lp_last_error": (C.c_char_p, []),
         "b200lp_version": (C.c_char_p, []),
     }

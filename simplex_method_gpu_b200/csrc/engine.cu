@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -51,6 +52,7 @@ struct b200lp_engine {
 	virtual int ipc_export(void* out) = 0;
 	virtual int ipc_import(const void* all, int nranks) = 0;
 	virtual int shard_rows(int64_t* row0, int64_t* rows) = 0;
+	virtual int download_profile(uint64_t* out, int64_t cap_iters, int64_t* n_iters) = 0;
 	cudaStream_t stream = nullptr;
 	int rank = 0, nranks = 1;
 	int grid = 0;
@@ -79,8 +81,6 @@ public:
 		for (int r = 0; r <= nranks; ++r) d.rowstart[r] = std::min<long long>(d.ld, (long long)r * rpr);
 		d.row0 = d.rowstart[rank];
 		d.ldb = d.rowstart[rank + 1] - d.rowstart[rank];
-		d.k0 = m * rank / nranks;
-		d.k1 = m * (rank + 1) / nranks;
 		d.nchunk = (int)((m + CHUNK - 1) / CHUNK);
 		d.nslice = (int)((m + SLICE - 1) / SLICE);
 		d.eps = sizeof(T) == 4 ? (double)(float)o.eps : o.eps;
@@ -108,8 +108,8 @@ public:
 		for (auto& v : vecs) CU(alloc(&v, ld));
 		d.b = vecs[0]; hb = vecs[0];
 		d.y = vecs[1]; d.x_b = vecs[2]; d.c_b = vecs[3]; d.E_q = vecs[4]; d.acol = vecs[5];
-		// mailbox: [XHdr][alpha ld][row_q ld]; peers store into it in sharded mode (IPC-exported)
-		mbox_bytes = sizeof(XHdr) + 2 * ld * sizeof(T);
+		// mailbox: [XHdr][alpha ld][row_q ld][row_q.b slice partials]; peers store into it in sharded mode (IPC-exported)
+		mbox_bytes = sizeof(XHdr) + (2 * ld + (size_t)d.nslice + 64) * sizeof(T);
 		CU(alloc(&mbox, mbox_bytes));
 		CU(cudaMemsetAsync(mbox, 0, mbox_bytes, stream));
 		d.alpha = reinterpret_cast<T*>(mbox + sizeof(XHdr));
@@ -120,16 +120,28 @@ public:
 		d.c = hcst;
 		CU(alloc(&d.alpha_part, (size_t)d.nchunk * (size_t)d.ldb));
 		CU(alloc(&d.dpart, (size_t)2 * d.nslice));
+		d.dpart0 = nranks > 1 ? d.row_q + ld : d.dpart;
 		CU(alloc(&d.b_ixs, m));
 		CU(alloc(&d.ctl, 1));
 		CU(alloc(&d.trace, (size_t)d.trace_cap));
 		CU(cudaMemsetAsync(d.ctl, 0, sizeof(Ctl), stream));
 		CU(cudaMallocHost(&pinned, sizeof(Ctl) + 64));
+		if (opt.profile > 0) {
+			d.prof_cap = std::min<int64_t>(opt.profile, 1 << 16);
+			CU(alloc(&d.prof, (size_t)d.prof_cap * NSTAMP));
+		}
 
 		// persistent grid: co-resident CTAs only (cooperative launch)
+		// the pricing ring lives in dynamic shared memory (above the 48 KB default limit)
+		for (const void* fn : {(const void*)simplex_persistent<T, 1>, (const void*)simplex_persistent<T, 2>,
+				(const void*)simplex_persistent<T, 4>, (const void*)simplex_persistent<T, 8>,
+				(const void*)simplex_persistent_sharded<T, 1>, (const void*)simplex_persistent_sharded<T, 2>,
+				(const void*)simplex_persistent_sharded<T, 4>, (const void*)simplex_persistent_sharded<T, 8>,
+				(const void*)k_price<T>})
+			CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_BYTES));
 		int occ = 0;
-		if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, 0));
-		else            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, 0));
+		if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, DYN_SMEM_BYTES));
+		else            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, DYN_SMEM_BYTES));
 		if (occ < 1) return fail(B200LP_ERR_CUDA, "persistent kernel does not fit on an SM");
 		max_grid = occ * num_sms;
 		const double work = (double)d.ld * (double)d.n / nranks;
@@ -142,15 +154,16 @@ public:
 		CU(alloc(&d.cand, (size_t)max_grid + 2));
 		CU(alloc(&d.cnt, (size_t)max_grid + 2));
 
-		// tile shape of the update+FTRAN pass: widest row tile that still gives every CTA a tile
+		// tile shape of the update+FTRAN pass: tiles are handed out dynamically, so the tallest row
+		// tile that still leaves every CTA ~100 tiles keeps the tail of the pass well under 1 %
+		// (measured: C3 best with 64-row tiles, C4 with 128-row tiles)
 		wc = 8;
 		for (int cand_wc : {1, 2, 4, 8}) {
 			const long long tr = (long long)(NWARP / cand_wc) * 32 * VecT<T>::N;
 			const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
-			if (tiles >= grid) { wc = cand_wc; break; }
+			if (tiles >= 96LL * grid) { wc = cand_wc; break; }
 		}
 		if (opt.tile_shape == 1 || opt.tile_shape == 2 || opt.tile_shape == 4 || opt.tile_shape == 8) wc = opt.tile_shape;
-		if (nranks > 1 && wc != 1) wc = 8;       // the sharded kernel is instantiated for the two extreme shapes
 		return B200LP_OK;
 	}
 
@@ -246,19 +259,24 @@ public:
 		if (opt.mode == 1 && nranks == 1) return run_phases(iters);
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
+		if (d.prof_cap > 0) CU(cudaMemsetAsync(d.prof, 0, (size_t)d.prof_cap * NSTAMP * sizeof(unsigned long long), stream));
+		prof_iter0 = hc.iter;
 		CU(cudaEventRecord(ev0, stream));
 		void* args[] = {&d};
 		const void* fn;
 		if (nranks > 1) {
 			if (!peers_mapped) return fail(B200LP_ERR_STATE, "sharded engine: ipc_import has not been called");
-			fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1> : (const void*)simplex_persistent_sharded<T, 8>;
+			fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1>
+			   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2>
+			   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4>
+			             : (const void*)simplex_persistent_sharded<T, 8>;
 		} else {
 			fn = wc == 1 ? (const void*)simplex_persistent<T, 1>
 			   : wc == 2 ? (const void*)simplex_persistent<T, 2>
 			   : wc == 4 ? (const void*)simplex_persistent<T, 4>
 			             : (const void*)simplex_persistent<T, 8>;
 		}
-		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, 0, stream));
+		CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, DYN_SMEM_BYTES, stream));
 		launches++;
 		CU(cudaEventRecord(ev1, stream));
 		return B200LP_OK;
@@ -274,7 +292,7 @@ public:
 			CU(pull_ctl());
 		}
 		in_flight = false;
-		if (hc.bad) return fail(B200LP_ERR_CUDA, "sharded engine: a peer GPU did not reach the exchange barrier within 20 s");
+		if (hc.bad) return fail(B200LP_ERR_CUDA, "sharded engine: a peer GPU did not answer within 20 s (the engine must be destroyed)");
 		if (res) {
 			std::memset(res, 0, sizeof(*res));
 			res->status = hc.status;
@@ -342,7 +360,8 @@ public:
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
 		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
 		CU(cudaSetDevice(opt.device));
-		k_price<T><<<grid, NT, 0, stream>>>(d);
+		CU(zero_tickets());
+		k_price<T><<<grid, NT, DYN_SMEM_BYTES, stream>>>(d);
 		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 0);
 		launches += 2;
 		CU(cudaGetLastError());
@@ -416,6 +435,17 @@ public:
 		return B200LP_OK;
 	}
 
+	// phase stamps of the last persistent launch: NSTAMP globaltimer values per iteration
+	int download_profile(uint64_t* out, int64_t cap_iters, int64_t* n_iters) override {
+		if (d.prof_cap == 0) return fail(B200LP_ERR_STATE, "engine was created without options.profile");
+		CU(cudaSetDevice(opt.device));
+		CU(cudaStreamSynchronize(stream));
+		const int64_t k = std::max<int64_t>(0, std::min<int64_t>({cap_iters, (int64_t)d.prof_cap, (int64_t)(hc.iter - prof_iter0)}));
+		if (k > 0 && out) CU(cudaMemcpy(out, d.prof, (size_t)k * NSTAMP * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		if (n_iters) *n_iters = k;
+		return B200LP_OK;
+	}
+
 	int64_t bytes_per_pivot() const override {
 		return (int64_t)sizeof(T) * (2 * d.m * d.m + d.m * (d.n - d.m));
 	}
@@ -467,6 +497,10 @@ private:
 		d.ns = ns_new;
 		d.nsl = nsl_new;
 		d.col0 = d.colstart[rank];
+		// unit (slack) columns priced without matrix bytes: none when the slack block was not recognised
+		const long long nunit = d.n - ns_new;
+		d.k0 = nunit * rank / nranks;
+		d.k1 = nunit * (rank + 1) / nranks;
 		ns = ns_new;
 		return cudaSuccess;
 	}
@@ -515,6 +549,8 @@ private:
 		Ctl* st = static_cast<Ctl*>(pinned);
 		*st = hc;
 		st->bar = 0;
+		st->price_ctr = st->upd_ctr = 0;
+		st->xarr[0] = st->xarr[1] = st->xarr[2] = 0;
 		cudaError_t e = cudaMemcpyAsync(d.ctl, st, sizeof(Ctl), cudaMemcpyHostToDevice, stream);
 		if (e != cudaSuccess) return e;
 		// the staging buffer is reused: make sure the copy has been consumed
@@ -536,15 +572,23 @@ private:
 		return cudaSuccess;
 	}
 
+	// work-ticket counters of the pricing / update phases (the persistent kernel resets them itself)
+	cudaError_t zero_tickets() {
+		static_assert(offsetof(Ctl, upd_ctr) == offsetof(Ctl, price_ctr) + sizeof(unsigned int), "adjacent counters");
+		return cudaMemsetAsync(reinterpret_cast<unsigned char*>(d.ctl) + offsetof(Ctl, price_ctr), 0, 2 * sizeof(unsigned int), stream);
+	}
+
 	void launch_update_ftran(bool update, bool ftran, long long p) {
+		zero_tickets();
 		const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
 		const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
 		const int g = (int)std::max<long long>(1, std::min<long long>(tiles, grid));
+		const int rev = (int)(hc.pivots & 1);
 #define LAUNCH_UF(WC_)                                                                                    \
 		do {                                                                                              \
-			if (update && ftran) k_update_ftran<T, WC_, true, true><<<g, NT, 0, stream>>>(d, p);          \
-			else if (update)     k_update_ftran<T, WC_, true, false><<<g, NT, 0, stream>>>(d, p);         \
-			else                 k_update_ftran<T, WC_, false, true><<<g, NT, 0, stream>>>(d, p);         \
+			if (update && ftran) k_update_ftran<T, WC_, true, true><<<g, NT, 0, stream>>>(d, p, rev);          \
+			else if (update)     k_update_ftran<T, WC_, true, false><<<g, NT, 0, stream>>>(d, p, rev);         \
+			else                 k_update_ftran<T, WC_, false, true><<<g, NT, 0, stream>>>(d, p, rev);         \
 		} while (0)
 		if (wc == 1) LAUNCH_UF(1); else if (wc == 2) LAUNCH_UF(2); else if (wc == 4) LAUNCH_UF(4); else LAUNCH_UF(8);
 #undef LAUNCH_UF
@@ -594,6 +638,7 @@ private:
 	int num_sms = 0, max_grid = 0, wc = 1;
 	bool have_data = false, in_flight = false;
 	int64_t launches = 0;
+	long long prof_iter0 = 0;
 };
 
 template <typename T>
@@ -728,6 +773,9 @@ int b200lp_ipc_export(b200lp_engine* e, void* out) { NEED(e); if (!out) return f
 int b200lp_ipc_import(b200lp_engine* e, const void* all, int32_t nranks) { NEED(e); if (!all) return fail(B200LP_ERR_ARG, "handles are NULL"); return e->ipc_import(all, nranks); }
 int b200lp_shard_rows(b200lp_engine* e, int64_t* row0, int64_t* rows) { NEED(e); return e->shard_rows(row0, rows); }
 int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols) { NEED(e); return e->shard_columns(col0, ncols); }
+int b200lp_profile_stamps(void) { return NSTAMP; }
+const char* b200lp_profile_names(void) { return PROFILE_NAMES_JSON; }
+int b200lp_download_profile(b200lp_engine* e, uint64_t* out, int64_t cap_iters, int64_t* n_iters) { NEED(e); return e->download_profile(out, cap_iters, n_iters); }
 int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int64_t ncols, const void* b, const void* c) {
 	NEED(e);
 	if (!Acols || !b || !c) return fail(B200LP_ERR_ARG, "Acols, b, c must not be NULL");

@@ -42,6 +42,12 @@ constexpr int CHUNK = 256;    // FTRAN partial-sum chunk (columns)
 constexpr int SUBW = 32;      // FTRAN sub-block (columns)
 constexpr int SLICE = 256;    // O(m) dot slice (elements)
 constexpr int PRICE_NC = 4;   // columns priced together by one CTA
+constexpr int PRICE_TAIL = 0;  // columns per CTA priced one at a time at the end of the pass; measured on B200: single-column
+                               // blocks are bound by the per-block ring overhead (half the streaming rate), which costs more
+                               // than the shorter tail saves, so only a ragged remainder (< PRICE_NC columns) goes this way
+constexpr int PRICE_STAGES = 4;                       // TMA ring depth of the pricing stream
+constexpr int PRICE_STAGE_BYTES = (PRICE_NC + 1) * NT * 16; // one stage: y + PRICE_NC columns, NT 16-byte vectors of rows each
+constexpr int DYN_SMEM_BYTES = PRICE_STAGES * PRICE_STAGE_BYTES;
 constexpr int MIN_CTAS = 2;   // resident CTAs per SM the persistent kernel is compiled for
 constexpr int MAXR = 8;       // ranks (GPUs) of one NVSwitch box
 
@@ -64,7 +70,10 @@ struct Ctl {
 	int status;               // B200LP_STATUS_*
 	int pending;              // rank-1 update (E_q, row_q) not yet applied to B^-1
 	int done;                 // optimum / unbounded reached
-	int bad;                  // peer barrier timed out (sharded mode)
+	int bad;                  // a wait timed out (sharded mode)
+	unsigned long long xarr[3];       // arrivals at the three exchanges (reset by the host before a launch)
+	unsigned int price_ctr;   // dynamic work tickets of the pricing phase (column groups)
+	unsigned int upd_ctr;     // dynamic work tickets of the update+FTRAN phase (tiles)
 	unsigned long long xepoch; // cross-GPU barrier epoch, monotonic over the engine's life
 	long long p, q;           // last entering column / leaving row
 	double min_e;             // last pricing minimum
@@ -99,16 +108,28 @@ struct Dev {
 	long long col0, nsl;
 	long long k0, k1;                 // share of the unit (slack) columns priced on this rank
 	long long colstart[MAXR + 1], rowstart[MAXR + 1];
+	unsigned long long* prof;         // optional phase stamps (globaltimer ns), NSTAMP per iteration of a launch
+	long long prof_cap;               // iterations the buffer holds (0 = profiling off)
 	const T* A_peer[MAXR];            // every rank's A shard (peer-mapped over NVLink)
-	unsigned char* mbox_peer[MAXR];   // every rank's mailbox: [XHdr][alpha ld][row_q ld]; alpha/row_q above point into our own
+	unsigned char* mbox_peer[MAXR];   // every rank's mailbox: [XHdr][alpha ld][row_q ld][rqb nslice]; alpha/row_q above point into our own
+	const T* dpart0;                  // row_q.b slice partials: dpart on one GPU, the mailbox's rqb when sharded
 	T* acol;                          // local copy of the entering column (sharded mode only)
 };
 
-// head of a rank's mailbox; peers store into it over NVLink
+// head of a rank's mailbox; peers store into it over NVLink.  Every record carries its own flag
+// (= the serial number of the pricing round it belongs to, monotonic over the engine's life), so
+// receiving a record is one acquire-load spin and needs no separate barrier.
+struct XCand {
+	double val;
+	long long idx;
+	long long cnt;
+	unsigned long long flag;
+};
 struct XHdr {
-	unsigned long long xflag[MAXR];   // xflag[r] = last barrier epoch rank r has signalled to us
-	Cand candx[MAXR];                 // candx[r] = rank r's pricing candidate
-	unsigned long long pad[8];
+	XCand pc[2][MAXR];                // X1: pricing candidate of rank r (double buffered by round parity)
+	XCand rc[MAXR];                   // X2: ratio candidate + eligible count of rank r's rows; flag also says "alpha slice stored"
+	unsigned long long rflag;         // X3: row q and its row_q.b slice partials are stored
+	unsigned long long pad[31];
 };
 static_assert(sizeof(XHdr) % 256 == 0, "mailbox vectors must stay 16-byte aligned");
 
@@ -190,7 +211,84 @@ struct Smem {
 	long long bc_i;
 	long long bc_c;
 	double bc_s[2];
+	long long tk;                     // update_ftran: next dynamic tile
+	double xv[MAXR];                  // sharded: records gathered from the mailbox
+	long long xi[MAXR];
+	long long xc[MAXR];
+	// pricing ring: TMA bulk copies land in dynamic shared memory, one mbarrier pair per stage
+	unsigned long long full[PRICE_STAGES];
+	unsigned long long empty[PRICE_STAGES];
+	long long ring_group[PRICE_STAGES];   // column group held by the stage, -1 = end of stream
+	int ring_rb[PRICE_STAGES];            // row block of that group
 };
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+	const unsigned a = smem_u32(bar);
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy global accesses (and those it has acquired) with later
+// async-proxy ones (TMA reads of y, which the previous pivot wrote with plain stores)
+__device__ __forceinline__ void fence_proxy_async_global() {
+	asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// global -> shared bulk copy (TMA, 1-D): completes `bytes` transaction bytes on `bar`; 16-byte aligned everything
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// same copy carrying an L2 eviction-priority hint (read-once streams must not push B^-1 out of L2)
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar,
+		unsigned long long policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+		::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+// ring position, identical in every thread of the CTA; survives from one pricing phase to the next
+struct Ring {
+	int stage;
+	unsigned phase;
+	__device__ __forceinline__ void advance() { if (++stage == PRICE_STAGES) { stage = 0; phase ^= 1u; } }
+};
+
+__device__ __forceinline__ void ring_init(Smem& sh, Ring& cons, Ring& prod) {
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < PRICE_STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NWARP); }
+		mbar_fence_init();
+	}
+	cons.stage = prod.stage = 0;
+	cons.phase = prod.phase = 0;
+	__syncthreads();
+}
 
 // block-wide argmin; result valid in every thread
 __device__ __forceinline__ void block_argmin(double& v, long long& i, Smem& sh) {
@@ -203,6 +301,30 @@ __device__ __forceinline__ void block_argmin(double& v, long long& i, Smem& sh) 
 #pragma unroll
 	for (int w = 1; w < NWARP; ++w)
 		if (cand_better(sh.red_v[w], sh.red_i[w], v, i)) { v = sh.red_v[w]; i = sh.red_i[w]; }
+}
+
+// ---------------------------------------------------------------- phase stamps
+
+constexpr int NSTAMP = 16;
+// interval j runs from stamp j to stamp j+1 (the last one to stamp 0 of the next iteration)
+#define PROFILE_NAMES_JSON \
+	"{\"single\": [\"price\", \"barrier + argmin p\", \"update + FTRAN\", \"barrier\", \"ratio\", " \
+	"\"barrier + argmin q\", \"book1 (row_q, E_q, dots)\", \"barrier\", \"book2 (x_b, y)\", \"barrier\"], " \
+	"\"sharded\": [\"price\", \"X1: arrive, publish candidate, gather\", \"fetch a_p + barrier\", \"update + FTRAN\", " \
+	"\"barrier\", \"X2: alpha + ratio of local rows, publish, gather\", \"book1 (E_q, dots; owner: row_q push)\", " \
+	"\"barrier + X3 flag\", \"book2 (x_b, y)\", \"barrier\"]}"
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+// CTA 0 / thread 0 stamps the time at which it passes point k of iteration `itl` of this launch
+template <typename T>
+__device__ __forceinline__ void stamp(const Dev<T>& d, long long itl, int k) {
+	if (d.prof_cap > 0 && blockIdx.x == 0 && threadIdx.x == 0 && itl < d.prof_cap)
+		d.prof[itl * NSTAMP + k] = globaltimer_ns();
 }
 
 // ---------------------------------------------------------------- grid barrier
@@ -250,62 +372,124 @@ __device__ __forceinline__ long long reduce_counts(const long long* cnt, int n, 
 
 // ---------------------------------------------------------------- phase: pricing
 
-// e_j = y.A_j - c_j for the ns dense columns (CTA b owns a contiguous column
-// range), e_j = y_k - c_j for the unit columns, fused with the argmin.
-// Replaces cublasSgemm(M=1) + cub::DeviceReduce::ArgMin (v4:289-294).
+// e_j = y.A_j - c_j for the ns dense columns, e_j = y_k - c_j for the unit columns, fused
+// with the argmin.  Replaces cublasSgemm(M=1) + cub::DeviceReduce::ArgMin (v4:289-294).
+//
+// A is streamed through a PRICE_STAGES-deep shared-memory ring by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx): one block = PRICE_NC columns x RB rows, RB = NT
+// 16-byte vectors, i.e. one row step of the whole CTA.  Thread 0 is the producer and runs
+// PRICE_STAGES-1 blocks ahead of the consumers (all NT threads, itself included), across
+// column-group boundaries, so HBM requests never drain while a group is being reduced.
+// Column groups are handed out dynamically: the first one is the CTA's index, the others
+// come from a ticket counter, which evens out slow and fast SMs.  Groups are PRICE_NC columns
+// wide; a ragged remainder goes one column at a time.
+// The summation order of a column does not depend on any of this (see the file header).
 template <typename T>
-__device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
-	using M = Mem<T>;
+__device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, Ring& cons, Ring& prod, int part, int nparts) {
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
+	constexpr int RB = NT * VN;               // rows per block
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const long long ld = d.ld;
+	const long long ntail0 = d.nsl < (long long)PRICE_TAIL * nparts ? d.nsl : (long long)PRICE_TAIL * nparts;
+	const long long nquad = (d.nsl - ntail0) / PRICE_NC;          // full-width groups
+	const long long ngroups = nquad + (d.nsl - nquad * PRICE_NC);  // + single columns
+	const int nrb = (int)((ld + RB - 1) / RB);
 
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 
-	const long long c0 = d.nsl * part / nparts, c1 = d.nsl * (part + 1) / nparts;   // local columns
-	int buf = 0;
-	for (long long col = c0; col < c1; col += PRICE_NC, buf ^= 1) {
-		const T* ap[PRICE_NC];
-#pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k) {
-			const long long cc = col + k < c1 ? col + k : c1 - 1;   // ragged tail: re-read the last column
-			ap[k] = d.A + cc * ld;
-		}
-		T acc[PRICE_NC][VN];
-#pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k)
-#pragma unroll
-			for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
-
-#pragma unroll 4
-		for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
-			const V yv = *reinterpret_cast<const V*>(d.y + i);
-			V av[PRICE_NC];
-#pragma unroll
-			for (int k = 0; k < PRICE_NC; ++k) av[k] = M::ld_nc(ap[k] + i);
+	// ---- producer cursor (meaningful in thread 0 only)
+	const unsigned long long pol_stream = l2_policy_evict_first();   // A is read once per pivot
+	long long pg = part, pnext = ngroups;
+	int prb = 0;
+	bool pend = false;
+	auto produce = [&]() {
+		mbar_wait(&sh.empty[prod.stage], prod.phase ^ 1u);       // consumers have released the stage
+		if (pg >= ngroups) {
+			sh.ring_group[prod.stage] = -1;                        // end of this CTA's stream
+			mbar_arrive(&sh.full[prod.stage]);
+			pend = true;
+		} else {
+			if (prb == 0) pnext = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // used nrb blocks later
+			const long long r0 = (long long)prb * RB;
+			const unsigned colbytes = (unsigned)((ld - r0 < RB ? ld - r0 : RB) * (long long)sizeof(T));
+			const int nc = pg < nquad ? PRICE_NC : 1;
+			const long long c0 = pg < nquad ? pg * PRICE_NC : nquad * PRICE_NC + (pg - nquad);
+			sh.ring_group[prod.stage] = pg;
+			sh.ring_rb[prod.stage] = prb;
+			mbar_arrive_expect_tx(&sh.full[prod.stage], (unsigned)(nc + 1) * colbytes);
+			unsigned char* dst = ringbuf + prod.stage * PRICE_STAGE_BYTES;
+			tma_load_1d(dst, d.y + r0, colbytes, &sh.full[prod.stage]);
 #pragma unroll
 			for (int k = 0; k < PRICE_NC; ++k)
-#pragma unroll
-				for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][v]);
+				if (k < nc)
+					tma_load_1d_hint(dst + (k + 1) * (NT * 16), d.A + (c0 + k) * ld + r0, colbytes, &sh.full[prod.stage], pol_stream);
+			if (++prb == nrb) { prb = 0; pg = pnext; }
 		}
+		prod.advance();
+	};
+	if (tid == 0) {
+		fence_proxy_async_global();
+		for (int k = 0; k < PRICE_STAGES - 1 && !pend; ++k) produce();
+	}
+
+	// ---- consumers
+	T acc[PRICE_NC][VN];
+	int crb = 0, buf = 0;
+	while (true) {
+		if (tid == 0 && !pend) produce();
+		const bool act = (long long)crb * RB + (long long)tid * VN < ld;
+		mbar_wait(&sh.full[cons.stage], cons.phase);
+		const long long g = sh.ring_group[cons.stage];
+		const int nc = g < nquad ? PRICE_NC : 1;
+		if (g >= 0) {
+			if (crb == 0) {
 #pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k) {
-			T s = acc[k][0];
+				for (int k = 0; k < PRICE_NC; ++k)
 #pragma unroll
-			for (int v = 1; v < VN; ++v) s = s + acc[k][v];
-			s = warp_butterfly_sum(s);
-			if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
+					for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
+			}
+			if (act) {
+				const unsigned char* src = ringbuf + cons.stage * PRICE_STAGE_BYTES + tid * 16;
+				const V yv = *reinterpret_cast<const V*>(src);
+#pragma unroll
+				for (int k = 0; k < PRICE_NC; ++k) {
+					if (k < nc) {
+						const V av = *reinterpret_cast<const V*>(src + (k + 1) * (NT * 16));
+#pragma unroll
+						for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(Mem<T>::get(av, v), Mem<T>::get(yv, v), acc[k][v]);
+					}
+				}
+			}
 		}
-		__syncthreads();
-		if (tid < PRICE_NC && col + tid < c1) {
-			T s = (T)sh.wsum[buf][tid][0];
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&sh.empty[cons.stage]);         // this warp is done with the stage
+		cons.advance();
+		if (g < 0) break;
+		if (++crb == nrb) {
+			crb = 0;
 #pragma unroll
-			for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
-			const long long j = d.col0 + col + tid;     // global column index
-			const double e = (double)(s - d.c[j]);
-			if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
+			for (int k = 0; k < PRICE_NC; ++k) {
+				if (k < nc) {
+					T s = acc[k][0];
+#pragma unroll
+					for (int v = 1; v < VN; ++v) s = s + acc[k][v];
+					s = warp_butterfly_sum(s);
+					if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
+				}
+			}
+			__syncthreads();
+			if (tid < nc) {
+				T s = (T)sh.wsum[buf][tid][0];
+#pragma unroll
+				for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
+				const long long c0 = g < nquad ? g * PRICE_NC : nquad * PRICE_NC + (g - nquad);
+				const long long j = d.col0 + c0 + tid;               // global column index
+				const double e = (double)(s - d.c[j]);
+				if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
+			}
+			buf ^= 1;
 		}
 	}
 
@@ -330,7 +514,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 // WR*32*VN rows x CHUNK columns.  row_q[chunk] and a_p[chunk] are staged in
 // shared memory.  alpha_part[chunk][row] receives the chunk partial.
 template <typename T, int WC, bool UPDATE, bool FTRAN>
-__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, long long uk, int part, int nparts) {
+__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, long long uk, bool reverse, int part, int nparts) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
@@ -349,21 +533,29 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, lon
 	T* stage_a = reinterpret_cast<T*>(sh.stage[1]);
 	const bool unit = acol == nullptr;     // entering column is the unit vector e_uk
 
-	for (long long tile = part; tile < ntiles; tile += nparts) {
+	// tiles are handed out dynamically: the first one is the CTA's index, the others come from a
+	// ticket counter (results do not depend on which CTA computes a tile).  Every other pass walks
+	// the tiles backwards, so the part of B^-1 that is still in L2 from the previous pass (up to
+	// the L2 capacity, dirty lines included) is touched first and never makes the trip to HBM.
+	long long ticket = part;
+	while (ticket < ntiles) {
+		const long long tile = reverse ? ntiles - 1 - ticket : ticket;
 		const long long rt = tile % ntr, ck = tile / ntr;
 		const long long j0 = ck * CHUNK;
 		__syncthreads();
+		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->upd_ctr, 1u);
 		{
 			const long long j = j0 + tid;     // NT == CHUNK
 			T r = T(0), a = T(0);
 			if (j < m) {
-				if (UPDATE) r = d.row_q[j];
+				if (UPDATE) r = __ldcg(d.row_q + j);      // mailbox data (peer-written when sharded): read at L2
 				if (FTRAN) a = unit ? (j == uk ? T(1) : T(0)) : acol[j];   // plain load: acol may have been written by this kernel
 			}
 			stage_rq[tid] = r;
 			stage_a[tid] = a;
 		}
 		__syncthreads();
+		const long long next_ticket = sh.tk;
 
 		const long long row = rt * TR + (long long)wr * 32 * VN + (long long)lane * VN;
 		const bool active = row < ld;     // warp uniform (ld is a multiple of 32*VN)
@@ -463,7 +655,24 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, lon
 				}
 			}
 		}
+		ticket = next_ticket;
 	}
+}
+
+// alpha_i = sum over the FTRAN chunks of alpha_part[ck][i], strictly left to right; the loads of
+// 16 chunks are issued together (predicated, no serial remainder), only the adds are ordered
+template <typename T>
+__device__ __forceinline__ T sum_chunk_partials(const T* part0, long long stride, int nchunk) {
+	T a = __ldcg(part0);
+	for (int c0 = 1; c0 < nchunk; c0 += 16) {
+		T v[16];
+#pragma unroll
+		for (int u = 0; u < 16; ++u) v[u] = c0 + u < nchunk ? __ldcg(part0 + (long long)(c0 + u) * stride) : T(0);
+#pragma unroll
+		for (int u = 0; u < 16; ++u)
+			if (c0 + u < nchunk) a = a + v[u];
+	}
+	return a;
 }
 
 // ---------------------------------------------------------------- phase: ratio test
@@ -480,9 +689,7 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
 		T a;
 		if (FROM_PARTIALS) {
-			a = __ldcg(d.alpha_part + i);
-#pragma unroll 8
-			for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ldb + i);
+			a = sum_chunk_partials(d.alpha_part + i, d.ldb, d.nchunk);
 			d.alpha[i] = a;
 		} else {
 			a = d.alpha[i];   // already exchanged between the ranks
@@ -558,18 +765,20 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 	if (tid < 2) {
 		T a = T(0);
 #pragma unroll 8
-		for (int s = 0; s < d.nslice; ++s) a = a + __ldcg(d.dpart + (long long)tid * d.nslice + s);
+		const T* part = tid == 0 ? d.dpart0 : d.dpart + d.nslice;
+		for (int s = 0; s < d.nslice; ++s) a = a + __ldcg(part + s);
 		if (tid == 1) a += d.c[p] - (T)__ldcg(&d.ctl->c_b_q);
 		sh.bc_s[tid] = (double)a;
 	}
 	__syncthreads();
 	const T sx = (T)sh.bc_s[0], sy = (T)sh.bc_s[1];
 	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
-		const T eq = d.E_q[i], rq = d.row_q[i];
+		const T eq = d.E_q[i], rq = __ldcg(d.row_q + i);
 		d.x_b[i] = fma_t(sx, eq, d.x_b[i]);
 		d.y[i] = fma_t(sy, rq, d.y[i]);
 		if (i == q) { d.c_b[i] = d.c[p]; d.b_ixs[i] = (int)p; }
 	}
+	fence_proxy_async_global();     // y is read by TMA (async proxy) in the next pricing phase
 }
 
 // z = c_b . x_b in slice order (v4:365); single CTA
@@ -599,6 +808,9 @@ __device__ double objective(const Dev<T>& d, Smem& sh) {
 template <typename T, int WC>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char ringbuf[];
+	Ring rcons, rprod;
+	ring_init(sh, rcons, rprod);
 	Ctl* ctl = d.ctl;
 	const int G = gridDim.x, me = blockIdx.x;
 	unsigned long long epoch = 0;
@@ -610,35 +822,48 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	long long p = ctl->p, q = ctl->q;
 	double min_e = ctl->min_e;
 
+	const long long it0 = it;
 	while (it < it_end) {
 		// ---- pricing + entering column (v4:288-302)
-		price_phase<T>(d, sh, me, G);
+		stamp(d, it - it0, 0);
+		price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		stamp(d, it - it0, 1);
 		grid_barrier(ctl, epoch);
+		if (me == 0 && threadIdx.x == 0) ctl->price_ctr = 0;     // every CTA is past pricing; next use is barriers away
 		reduce_cands(d.cand, G, min_e, p, sh);
+		stamp(d, it - it0, 2);
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
 		// ---- pending rank-1 update fused with the FTRAN of column p
 		const T* acol = p < d.ns ? d.A + p * d.ld : nullptr;
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, acol, p - d.ns, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, acol, p - d.ns, me, G);
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, acol, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, acol, p - d.ns, pivots & 1, me, G);
 		pending = 0;
+		stamp(d, it - it0, 3);
 		grid_barrier(ctl, epoch);
+		if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
+		stamp(d, it - it0, 4);
 
 		// ---- ratio test (v4:311-325)
 		ratio_phase<T, true>(d, sh, me, G);
+		stamp(d, it - it0, 5);
 		grid_barrier(ctl, epoch);
 		double th;
 		reduce_cands(d.cand, G, th, q, sh);
 		const long long elig = reduce_counts(d.cnt, G, sh);
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
+		stamp(d, it - it0, 6);
 
 		// ---- pivot (v4:331-356)
 		book1_phase<T>(d, sh, p, q, me, G);
+		stamp(d, it - it0, 7);
 		grid_barrier(ctl, epoch);
+		stamp(d, it - it0, 8);
 		book2_phase<T>(d, sh, p, q, me, G);
 		if (me == 0 && threadIdx.x == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
 		pending = 1;
 		++pivots;
+		stamp(d, it - it0, 9);
 		++it;
 		grid_barrier(ctl, epoch);
 	}
@@ -660,11 +885,18 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 // b_ixs) is replicated, so all ranks take identical decisions and the per-row / per-column
 // sums are exactly the single-GPU ones (results are bit-identical for every GPU count).
 // Three exchanges per pivot, all direct peer stores over NVLink into the receivers'
-// mailboxes followed by a flag barrier — no NCCL call and no host on the data path:
-//   X1  pricing candidate (value, index), 16 B per rank            (replaces the global cub ArgMin)
-//   X2  alpha slices of the local row block, m/R values per rank   (after the fused update+FTRAN)
-//   X3  row q of B^-1 from its owner, m values                     (replaces cublasScopy, v4:331)
-// The entering column a_p is pulled from its owner's A shard with peer loads.
+// mailboxes — no NCCL call and no host on the data path:
+//   X1  pricing candidate (value, index) of the local column block      (replaces the global cub ArgMin)
+//   X2  alpha of the local row block (m/R values) + the ratio-test candidate of those rows
+//   X3  row q of B^-1 from its owner (m values) + the slice partials of row_q.b  (replaces cublasScopy, v4:331)
+// Each record carries its own flag: the LAST CTA of the sending rank to finish the producing
+// phase stores the record with a release at system scope, and every CTA of every rank spins
+// on the flags in its own mailbox.  That spin is the barrier — a pivot costs three NVLink
+// hops and four local grid barriers.  Ordering: payload stores by any CTA -> gpu-scope fence +
+// arrival (barrier or counter) -> acquired by the publishing thread -> st.release.sys of the
+// flag -> ld.acquire.sys by the receiver; release/acquire are cumulative in the PTX memory
+// model, so exactly ONE system-scope fence sits on the critical path of an exchange.  The entering column a_p is pulled from its owner's A
+// shard with peer loads.
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
 	unsigned long long v;
@@ -674,65 +906,97 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-	return t;
+
+constexpr unsigned long long XWAIT_NS = 20000000000ULL;   // 20 s: a peer died
+
+// spin until *flag >= want; false on time-out
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long* flag, unsigned long long want) {
+	if (ld_acquire_sys(flag) >= want) return true;
+	const unsigned long long t0 = globaltimer_ns();
+	while (ld_acquire_sys(flag) < want)
+		if (globaltimer_ns() - t0 > XWAIT_NS) return false;
+	return true;
 }
 
-// grid barrier whose release/acquire fences are system scope (peer stores must be
-// visible to the other GPUs before the flag that announces them)
-__device__ __forceinline__ void grid_barrier_sys(Ctl* ctl, unsigned long long& epoch) {
+// local grid barrier with a time-out (a CTA that gave up on a dead peer must not hang the others)
+__device__ __forceinline__ bool grid_barrier_t(Ctl* ctl, unsigned long long& epoch, Smem& sh) {
 	epoch += gridDim.x;
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		__threadfence_system();
+		bool ok = true;
 		if (gridDim.x > 1) {
+			__threadfence();
 			atomicAdd(&ctl->bar, 1ULL);
-			while (*((volatile unsigned long long*)&ctl->bar) < epoch) { }
+			const unsigned long long t0 = globaltimer_ns();
+			while (*((volatile unsigned long long*)&ctl->bar) < epoch)
+				if (globaltimer_ns() - t0 > XWAIT_NS) { ok = false; break; }
+			__threadfence();
 		}
-		__threadfence_system();
+		sh.bc_c = ok;
 	}
 	__syncthreads();
+	return sh.bc_c != 0;
 }
 
-// cross-GPU flag barrier, executed by CTA 0 between two grid_barrier_sys calls:
-// thread r signals rank r (store into ITS mailbox) and waits for rank r's signal in ours.
+// one arrival per CTA on a monotonic counter; true (in every thread) for the CTA that arrives last.
+// Data written before the call by any CTA is visible to the last one after it.
+__device__ __forceinline__ bool arrive_last(unsigned long long* ctr, unsigned long long target, Smem& sh) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const bool last = atomicAdd(ctr, 1ULL) + 1 == target;
+		__threadfence();
+		sh.bc_c = last;
+	}
+	__syncthreads();
+	const bool last = sh.bc_c != 0;
+	__syncthreads();
+	return last;
+}
+
+template <typename T> __device__ __forceinline__ XHdr* xhdr(const Dev<T>& d, int r) { return reinterpret_cast<XHdr*>(d.mbox_peer[r]); }
+template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int r) { return reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr)); }
+template <typename T> __device__ __forceinline__ T* xrowq(const Dev<T>& d, int r) { return xalpha(d, r) + d.ld; }
+template <typename T> __device__ __forceinline__ T* xrqb(const Dev<T>& d, int r) { return xalpha(d, r) + 2 * d.ld; }
+
+// collect the R records of one exchange from our own mailbox and reduce them: lexicographic
+// argmin over (val, idx), sum of cnt.  Same fixed order on every rank and CTA.
 template <typename T>
-__device__ __forceinline__ void xsync(const Dev<T>& d, unsigned long long xepoch) {
-	if (blockIdx.x != 0) return;
+__device__ __forceinline__ bool gather_records(const Dev<T>& d, const XCand* rec, unsigned long long e, Smem& sh,
+		double& v, long long& i, long long& c) {
 	if (threadIdx.x < d.nranks) {
-		const int r = threadIdx.x;
-		__threadfence_system();
-		st_release_sys(&reinterpret_cast<XHdr*>(d.mbox_peer[r])->xflag[d.rank], xepoch);
-		const unsigned long long* mine = &reinterpret_cast<XHdr*>(d.mbox_peer[d.rank])->xflag[r];
-		const unsigned long long t0 = globaltimer_ns();
-		while (ld_acquire_sys(mine) < xepoch) {
-			if (globaltimer_ns() - t0 > 20000000000ULL) { d.ctl->bad = 1; break; }   // 20 s: a peer died
-		}
-		__threadfence_system();
+		const XCand* r = rec + threadIdx.x;
+		const bool ok = wait_flag_sys(&r->flag, e);
+		sh.xv[threadIdx.x] = __ldcg(&r->val);
+		sh.xi[threadIdx.x] = __ldcg(&r->idx);
+		sh.xc[threadIdx.x] = ok ? __ldcg(&r->cnt) : -1;
 	}
 	__syncthreads();
+	v = CUDART_INF; i = LLONG_MAX; c = 0;
+	bool ok = true;
+	for (int r = 0; r < d.nranks; ++r) {
+		if (sh.xc[r] < 0) ok = false;
+		if (cand_better(sh.xv[r], sh.xi[r], v, i)) { v = sh.xv[r]; i = sh.xi[r]; }
+		c += sh.xc[r];
+	}
+	__syncthreads();
+	return ok;
 }
 
-// full exchange step: everything stored to peers before it is visible to them after it
+// the last CTA of this rank reduces the per-CTA candidates and stores the record into every mailbox
 template <typename T>
-__device__ __forceinline__ void xbarrier(const Dev<T>& d, unsigned long long& epoch, unsigned long long& xepoch) {
-	grid_barrier_sys(d.ctl, epoch);
-	xsync(d, ++xepoch);
-	grid_barrier_sys(d.ctl, epoch);
-}
-
-// X1: CTA 0 reduces this rank's per-CTA candidates and stores the winner into every mailbox
-template <typename T>
-__device__ void push_price_candidate(const Dev<T>& d, Smem& sh) {
-	if (blockIdx.x != 0) return;
+__device__ __forceinline__ void publish(const Dev<T>& d, Smem& sh, int which, int par, unsigned long long e, bool with_counts) {
 	double v; long long i;
 	reduce_cands(d.cand, gridDim.x, v, i, sh);
+	const long long c = with_counts ? reduce_counts(d.cnt, gridDim.x, sh) : 0;
 	if (threadIdx.x < d.nranks) {
-		Cand* dst = &reinterpret_cast<XHdr*>(d.mbox_peer[threadIdx.x])->candx[d.rank];
+		XHdr* h = xhdr(d, threadIdx.x);
+		XCand* dst = which == 0 ? &h->pc[par][d.rank] : &h->rc[d.rank];
 		dst->val = v;
 		dst->idx = i;
+		dst->cnt = c;
+		st_release_sys(&dst->flag, e);     // orders the three stores above (and, cumulatively, everything
+		                                   // the other CTAs fenced before they arrived) before the flag
 	}
 }
 
@@ -749,71 +1013,76 @@ __device__ void fetch_column(const Dev<T>& d, long long p, int part, int nparts)
 		*reinterpret_cast<V*>(d.acol + i) = M::ld_nc(src + i);
 }
 
-// X2: alpha of the local rows = sum of the chunk partials (left to right), stored into every rank's alpha
+// X2 producer: alpha of the local rows = sum of the chunk partials (left to right), stored into
+// every rank's alpha; the ratio test of those rows (v4:199-208) gives this CTA's candidate.
 template <typename T>
-__device__ void push_alpha_phase(const Dev<T>& d, int part, int nparts) {
-	const long long nloc = d.ldb;
-	for (long long i = (long long)part * NT + threadIdx.x; i < nloc; i += (long long)nparts * NT) {
-		T a = __ldcg(d.alpha_part + i);
-#pragma unroll 8
-		for (int ck = 1; ck < d.nchunk; ++ck) a = a + __ldcg(d.alpha_part + (long long)ck * d.ldb + i);
-		for (int r = 0; r < d.nranks; ++r)
-			reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr))[d.row0 + i] = a;
+__device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, int part, int nparts) {
+	const int tid = threadIdx.x;
+	double best_v = CUDART_INF;
+	long long best_i = LLONG_MAX;
+	long long elig = 0;
+	for (long long il = (long long)part * NT + tid; il < d.ldb; il += (long long)nparts * NT) {
+		const T a = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
+		const long long i = d.row0 + il;
+		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
+		if (i < d.m && a > T(0)) {
+			++elig;
+			const double th = (double)(d.x_b[i] / a);
+			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+		}
+	}
+	block_argmin(best_v, best_i, sh);
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) elig += __shfl_xor_sync(0xffffffffu, elig, off);
+	__syncthreads();
+	if ((tid & 31) == 0) sh.red_c[tid >> 5] = elig;
+	__syncthreads();
+	if (tid == 0) {
+		long long c = 0;
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) c += sh.red_c[w];
+		d.cand[part].val = best_v;
+		d.cand[part].idx = best_i;
+		d.cnt[part] = c;
 	}
 }
 
 // book1, sharded: E_q and the c_b.E_q slice partials on every rank (replicated data);
-// X3: the owner of row q gathers it from its B^-1 block and stores it into every rank's row_q.
+// X3 producer: the owner of row q gathers it from its B^-1 block, forms the row_q.b slice
+// partials and stores both into every rank's mailbox.
 template <typename T>
-__device__ void book1a_sharded(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
+__device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const T alpha_q = d.alpha[q];
+	const T alpha_q = __ldcg(d.alpha + q);     // mailbox data: read at L2
 	const T c_p = d.c[p];
 	const bool owner = q >= d.row0 && q < d.row0 + d.ldb;
 	for (long long s = part; s < d.nslice; s += nparts) {
 		const long long i = s * SLICE + tid;
-		T t2 = T(0);
+		T t1 = T(0), t2 = T(0);
 		if (i < d.m) {
-			const T eq = (i != q) ? (-d.alpha[i] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			const T eq = (i != q) ? (-__ldcg(d.alpha + i) / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
 			d.E_q[i] = eq;
 			T cb = d.c_b[i];
 			if (i == q) { d.ctl->c_b_q = (double)cb; cb = c_p; }
 			t2 = fma_t(cb, eq, T(0));
 			if (owner) {
 				const T rq = d.B[(q - d.row0) + i * d.ldb];
-				for (int r = 0; r < d.nranks; ++r)
-					(reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr)) + d.ld)[i] = rq;
+				t1 = fma_t(rq, d.b[i], T(0));
+				for (int r = 0; r < d.nranks; ++r) xrowq(d, r)[i] = rq;
 			}
 		}
+		t1 = warp_butterfly_sum(t1);
 		t2 = warp_butterfly_sum(t2);
 		__syncthreads();
-		if (lane == 0) sh.dsum[1][warp] = (double)t2;
+		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; }
 		__syncthreads();
 		if (tid == 0) {
-			T a = T(0);
+			T a1 = T(0), a2 = T(0);
 #pragma unroll
-			for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[1][w];
-			d.dpart[(long long)d.nslice + s] = a;
-		}
-	}
-}
-
-// row_q.b slice partials once row_q has arrived
-template <typename T>
-__device__ void book1b_sharded(const Dev<T>& d, Smem& sh, int part, int nparts) {
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for (long long s = part; s < d.nslice; s += nparts) {
-		const long long i = s * SLICE + tid;
-		T t1 = i < d.m ? fma_t(d.row_q[i], d.b[i], T(0)) : T(0);
-		t1 = warp_butterfly_sum(t1);
-		__syncthreads();
-		if (lane == 0) sh.dsum[0][warp] = (double)t1;
-		__syncthreads();
-		if (tid == 0) {
-			T a = T(0);
-#pragma unroll
-			for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[0][w];
-			d.dpart[s] = a;
+			for (int w = 0; w < NWARP; ++w) { a1 = a1 + (T)sh.dsum[0][w]; a2 = a2 + (T)sh.dsum[1][w]; }
+			d.dpart[(long long)d.nslice + s] = a2;
+			if (owner)
+				for (int r = 0; r < d.nranks; ++r) xrqb(d, r)[s] = a1;
 		}
 	}
 }
@@ -821,10 +1090,14 @@ __device__ void book1b_sharded(const Dev<T>& d, Smem& sh, int part, int nparts) 
 template <typename T, int WC>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T> d) {
 	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char ringbuf[];
+	Ring rcons, rprod;
+	ring_init(sh, rcons, rprod);
 	Ctl* ctl = d.ctl;
-	const int G = gridDim.x, me = blockIdx.x;
+	const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
 	unsigned long long epoch = 0;
-	unsigned long long xepoch = ctl->xepoch;
+	unsigned long long xe = ctl->xepoch;            // serial number of the last pricing round
+	unsigned long long n1 = 0, n2 = 0;              // arrival targets of X1 / X2 in this launch
 
 	long long it = ctl->iter, pivots = ctl->pivots;
 	const long long it_end = ctl->it_end;
@@ -832,66 +1105,74 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 	int status = 0, done = 0, bad = 0;
 	long long p = ctl->p, q = ctl->q;
 	double min_e = ctl->min_e;
-	const XHdr* mine = reinterpret_cast<const XHdr*>(d.mbox_peer[d.rank]);
+	const XHdr* mine = xhdr(d, d.rank);
 
+	const long long it0 = it;
 	while (it < it_end) {
-		// ---- pricing over the local column block, X1
-		price_phase<T>(d, sh, me, G);
-		grid_barrier_sys(ctl, epoch);
-		push_price_candidate<T>(d, sh);
-		xbarrier(d, epoch, xepoch);
-		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
-		min_e = CUDART_INF; p = LLONG_MAX;
-		for (int r = 0; r < d.nranks; ++r) {       // same fixed order on every rank and CTA
-			const double cv = __ldcg(&mine->candx[r].val);
-			const long long ci = __ldcg(&mine->candx[r].idx);
-			if (cand_better(cv, ci, min_e, p)) { min_e = cv; p = ci; }
-		}
+		// ---- pricing over the local column block; X1
+		stamp(d, it - it0, 0);
+		++xe;
+		const int par = (int)(xe & 1);
+		price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		stamp(d, it - it0, 1);
+		if (arrive_last(&ctl->xarr[0], n1 += G, sh)) publish(d, sh, 0, par, xe, false);
+		long long dummy;
+		if (!gather_records(d, mine->pc[par], xe, sh, min_e, p, dummy)) { bad = 1; break; }
+		if (me == 0 && tid == 0) ctl->price_ctr = 0;       // every local CTA is past pricing
+		stamp(d, it - it0, 2);
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
 		// ---- entering column from its owner, then the fused update + FTRAN on the local rows
 		const bool dense = p < d.ns;
 		if (dense) {
 			fetch_column<T>(d, p, me, G);
-			grid_barrier(ctl, epoch);
+			if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
 		}
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, me, G);
+		stamp(d, it - it0, 3);
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
 		pending = 0;
-		grid_barrier(ctl, epoch);
+		stamp(d, it - it0, 4);
+		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
+		if (me == 0 && tid == 0) ctl->upd_ctr = 0;
+		stamp(d, it - it0, 5);
 
-		// ---- X2: alpha slices to every rank, then the ratio test on the full alpha (replicated)
-		push_alpha_phase<T>(d, me, G);
-		xbarrier(d, epoch, xepoch);
-		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
-		ratio_phase<T, false>(d, sh, me, G);
-		grid_barrier(ctl, epoch);
+		// ---- X2: alpha slices to every rank together with the ratio test of the local rows (v4:311-325)
+		push_alpha_ratio<T>(d, sh, me, G);
+		if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, true);
 		double th;
-		reduce_cands(d.cand, G, th, q, sh);
-		const long long elig = reduce_counts(d.cnt, G, sh);
+		long long elig;
+		if (!gather_records(d, mine->rc, xe, sh, th, q, elig)) { bad = 1; break; }
+		stamp(d, it - it0, 6);
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
 
 		// ---- pivot: E_q everywhere, X3 row q from its owner, then the replicated O(m) updates
-		book1a_sharded<T>(d, sh, p, q, me, G);
-		xbarrier(d, epoch, xepoch);
-		if (*(volatile int*)&ctl->bad) { bad = 1; break; }
-		book1b_sharded<T>(d, sh, me, G);
-		grid_barrier(ctl, epoch);
+		book1_sharded<T>(d, sh, p, q, me, G);
+		stamp(d, it - it0, 7);
+		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
+		// owner: the row and its partials were stored by all local CTAs before the barrier; one
+		// system-scope release covers them (release is cumulative over what the barrier acquired)
+		if (me == 0 && tid < d.nranks && q >= d.row0 && q < d.row0 + d.ldb) st_release_sys(&xhdr(d, tid)->rflag, xe);
+		if (tid == 0) sh.bc_c = wait_flag_sys(&mine->rflag, xe);
+		__syncthreads();
+		if (!sh.bc_c) { bad = 1; break; }
+		stamp(d, it - it0, 8);
 		book2_phase<T>(d, sh, p, q, me, G);
-		if (me == 0 && threadIdx.x == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
+		if (me == 0 && tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
 		pending = 1;
 		++pivots;
+		stamp(d, it - it0, 9);
 		++it;
-		grid_barrier(ctl, epoch);
+		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
 	}
 
+	if (bad) { if (tid == 0) ctl->bad = 1; return; }
 	if (me == 0) {
 		const double z = objective<T>(d, sh);
-		if (threadIdx.x == 0) {
+		if (tid == 0) {
 			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
-			ctl->status = status; ctl->done = done; ctl->xepoch = xepoch;
+			ctl->status = status; ctl->done = done; ctl->xepoch = xe;
 			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
-			if (bad) ctl->bad = 1;
 		}
 	}
 }
@@ -903,7 +1184,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 template <typename T>
 __global__ void __launch_bounds__(NT) k_price(Dev<T> d) {
 	__shared__ Smem sh;
-	price_phase<T>(d, sh, blockIdx.x, gridDim.x);
+	extern __shared__ __align__(128) unsigned char ringbuf[];
+	Ring rcons, rprod;
+	ring_init(sh, rcons, rprod);
+	price_phase<T>(d, sh, ringbuf, rcons, rprod, blockIdx.x, gridDim.x);
 }
 
 // final argmin over the per-CTA candidates -> ctl->p / ctl->min_e (kind 0) or ctl->q + eligible (kind 1)
@@ -921,9 +1205,9 @@ __global__ void __launch_bounds__(NT) k_pick(Dev<T> d, int ncand, int kind) {
 }
 
 template <typename T, int WC, bool UPDATE, bool FTRAN>
-__global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p) {
+__global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p, int reverse) {
 	__shared__ Smem sh;
-	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, blockIdx.x, gridDim.x);
+	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
 }
 
 template <typename T>

@@ -186,6 +186,14 @@ class Engine:
         capi.check(self._L.b200lp_download_vector(self._h, which, _vp(out)))
         return out
 
+    def profile(self, cap: int = 1 << 16) -> np.ndarray:
+        """Phase time stamps (ns) of the last persistent launch, shape (iterations, stamps); needs profile=N."""
+        ns = self._L.b200lp_profile_stamps()
+        buf = np.zeros((cap, ns), np.uint64)
+        k = C.c_int64(0)
+        capi.check(self._L.b200lp_download_profile(self._h, _vp(buf), cap, C.byref(k)))
+        return buf[:k.value].copy()
+
     # -- single phases
     def phase_price(self):
         p, mn = C.c_int64(0), C.c_double(0)

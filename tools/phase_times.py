@@ -1,0 +1,87 @@
+"""Dev tool (GPU box): per-phase time breakdown INSIDE the persistent kernel, from the %globaltimer
+stamps CTA 0 records at every phase boundary (options.profile).  Single GPU:
+
+    python tools/phase_times.py --lp 8192x16384 --pivots 300
+
+Sharded (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29531 tools/phase_times.py --lp 32768x65536 --pivots 64
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simplex_method_gpu_b200 as lp  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--lp", default="8192x16384", help="MxN (not --m/--n: torchrun's argparse would grab them)")
+ap.add_argument("--pivots", type=int, default=300)
+ap.add_argument("--skip", type=int, default=20, help="leading pivots left out of the averages")
+ap.add_argument("--grid", type=int, default=0)
+ap.add_argument("--shape", type=int, default=0, help="update+FTRAN tile shape (warps along columns), 0 = auto")
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+a.m, a.n = (int(x) for x in a.lp.lower().split("x"))
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+names = json.loads(lp.capi.lib().b200lp_profile_names().decode())
+
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    from simplex_method_gpu_b200.sharded import ShardedEngine
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    e = ShardedEngine(a.m, a.n, np.float64, rank=rank, world=world, device=local, eps=1e-9, max_iter=1 << 30,
+                      profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape)
+    e.generate_dense(1)
+    e.connect()
+    dist.barrier()
+    names = names["sharded"]
+else:
+    e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape)
+    e.generate_dense(1)
+    names = names["single"]
+
+e.run(8)                                  # warm-up launch
+r0 = e.run(0)
+r = e.run(a.pivots)
+st = e.profile().astype(np.int64)         # (iterations, stamps)
+piv = r["pivots"] - r0["pivots"]
+k = len(names)
+st = st[a.skip:, :k]
+ok = (st > 0).all(axis=1)
+st = st[ok]
+# stamp j of iteration i+1 closes the last interval of iteration i
+nxt = np.roll(st[:, 0], -1)
+full = np.concatenate([st, nxt[:, None]], axis=1)[:-1]
+d = np.diff(full, axis=1) / 1e3           # us
+tot = d.sum(axis=1)
+lines = [f"rank {rank}/{world}  m={a.m} n={a.n} grid={e.grid_ctas}: {piv} pivots in {r['ms_solve']:.2f} ms "
+         f"({r['ms_solve'] / max(piv, 1) * 1e3:.1f} us/pivot by events); {len(d)} iterations averaged, "
+         f"{tot.mean():.1f} us/iteration by stamps"]
+for j in range(k):
+    lines.append(f"  {names[j]:<44s} {d[:, j].mean():8.2f} us  (min {d[:, j].min():7.2f}, max {d[:, j].max():7.2f})  "
+                 f"{100 * d[:, j].mean() / tot.mean():5.1f}%")
+text = "\n".join(lines)
+if world > 1:
+    import torch.distributed as dist
+    gathered = [None] * world
+    dist.all_gather_object(gathered, text)
+    text = "\n".join(gathered)
+if rank == 0:
+    print(text, flush=True)
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write(text + "\n")
+e.close()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
