@@ -66,11 +66,19 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        """Start of the timed region (the sampler itself is started earlier: nvidia-smi needs ~1 s to come up)."""
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -80,7 +88,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc:
@@ -93,7 +101,15 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if self.t0 is not None:
+            t1 = self.t1 if self.t1 is not None else time.time()
+            inside = [r for t, r in rows if self.t0 <= t <= t1 + 0.06]
+            # a window shorter than the sampling period: take the samples that bracket it
+            rows = inside if inside else [r for t, r in rows if self.t0 - 0.25 <= t <= t1 + 0.25]
+        else:
+            rows = [r for _, r in rows]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -122,14 +138,14 @@ def run_b200_single(args, wl):
     eng.generate_dense(SEED)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     # every step: back to the slack basis (untimed), then a window of P pivots (timed)
-    for _ in range(args.warmup):
-        eng.reset()
-        r = eng.run(P)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    piv0 = 0
     pivots_timed, launches, internal_ms = 0, 0, 0.0
-    torch.cuda.synchronize()
     with ClockSampler(dev) as clk:
+        for _ in range(args.warmup):
+            eng.reset()
+            r = eng.run(P)
+        torch.cuda.synchronize()
+        clk.mark_start()
         for a, b_ in ev:
             eng.reset()
             l0 = eng.run(0)["kernel_launches"]
@@ -142,6 +158,7 @@ def run_b200_single(args, wl):
             launches += r["kernel_launches"] - l0
             internal_ms += r["ms_solve"]
         torch.cuda.synchronize()
+        clk.mark_end()
     step_ms = [a.elapsed_time(b_) for a, b_ in ev]
     total_ms = float(sum(step_ms))
     value = pivots_timed / (total_ms * 1e-3)

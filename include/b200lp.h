@@ -62,6 +62,8 @@ typedef struct {
 	int32_t mode;         /* 0 = persistent cooperative kernel, 1 = one launch per phase */
 	int32_t profile;      /* > 0: record phase time stamps for the first `profile` iterations of every
 	                         persistent launch (b200lp_download_profile); 0 = off (default) */
+	int32_t price_cols;   /* pricing group width: 0 = auto, else 2 | 4 columns per TMA block */
+	int32_t reserved;
 } b200lp_options;
 
 typedef struct {

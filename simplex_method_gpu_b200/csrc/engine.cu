@@ -497,6 +497,10 @@ private:
 		d.ns = ns_new;
 		d.nsl = nsl_new;
 		d.col0 = d.colstart[rank];
+		// pricing group width
+		// (measured on B200: 2-column blocks run at ~60 % of the streaming rate of 4-column blocks, which costs
+		// more than their shorter tail saves, so auto is always 4)
+		d.price_nc = (opt.price_cols == 2 || opt.price_cols == 4) ? opt.price_cols : 4;
 		// unit (slack) columns priced without matrix bytes: none when the slack block was not recognised
 		const long long nunit = d.n - ns_new;
 		d.k0 = nunit * rank / nranks;
@@ -586,9 +590,9 @@ private:
 		const int rev = (int)(hc.pivots & 1);
 #define LAUNCH_UF(WC_)                                                                                    \
 		do {                                                                                              \
-			if (update && ftran) k_update_ftran<T, WC_, true, true><<<g, NT, 0, stream>>>(d, p, rev);          \
-			else if (update)     k_update_ftran<T, WC_, true, false><<<g, NT, 0, stream>>>(d, p, rev);         \
-			else                 k_update_ftran<T, WC_, false, true><<<g, NT, 0, stream>>>(d, p, rev);         \
+			if (update && ftran) k_update_ftran<T, WC_, true, true><<<g, NT, UF_SMEM_BYTES, stream>>>(d, p, rev);          \
+			else if (update)     k_update_ftran<T, WC_, true, false><<<g, NT, UF_SMEM_BYTES, stream>>>(d, p, rev);         \
+			else                 k_update_ftran<T, WC_, false, true><<<g, NT, UF_SMEM_BYTES, stream>>>(d, p, rev);         \
 		} while (0)
 		if (wc == 1) LAUNCH_UF(1); else if (wc == 2) LAUNCH_UF(2); else if (wc == 4) LAUNCH_UF(4); else LAUNCH_UF(8);
 #undef LAUNCH_UF

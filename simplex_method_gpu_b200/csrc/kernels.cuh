@@ -41,13 +41,18 @@ constexpr int NWARP = NT / 32;
 constexpr int CHUNK = 256;    // FTRAN partial-sum chunk (columns)
 constexpr int SUBW = 32;      // FTRAN sub-block (columns)
 constexpr int SLICE = 256;    // O(m) dot slice (elements)
-constexpr int PRICE_NC = 4;   // columns priced together by one CTA
-constexpr int PRICE_TAIL = 0;  // columns per CTA priced one at a time at the end of the pass; measured on B200: single-column
-                               // blocks are bound by the per-block ring overhead (half the streaming rate), which costs more
-                               // than the shorter tail saves, so only a ragged remainder (< PRICE_NC columns) goes this way
-constexpr int PRICE_STAGES = 4;                       // TMA ring depth of the pricing stream
-constexpr int PRICE_STAGE_BYTES = (PRICE_NC + 1) * NT * 16; // one stage: y + PRICE_NC columns, NT 16-byte vectors of rows each
-constexpr int DYN_SMEM_BYTES = PRICE_STAGES * PRICE_STAGE_BYTES;
+constexpr int PRICE_NC = 4;   // most columns priced together by one CTA (Dev::price_nc = 4 or 2 per problem)
+constexpr int PRICE_UNIT = NT * 16;                   // ring allocation unit: one vector (y or a column) of one row block
+constexpr int DYN_SMEM_BYTES = 20 * PRICE_UNIT;       // pricing ring: 4 stages of y + 4 columns (or 6 stages of y + 2 columns);
+                                                      // its first 12 KB double as the update+FTRAN staging area.
+                                                      // Measured: a 5th stage (100 KB) does not speed pricing up and slows the
+                                                      // update+FTRAN pass by 17 % — two CTAs would leave only ~23 KB of L1, and
+                                                      // the pass keeps 64 KB of loads per SM in flight through L1
+constexpr int UF_SMEM_BYTES = 2 * CHUNK * 8 + NWARP * 32 * 4 * 8; // row_q/a_p chunk + cross-warp combine
+constexpr int PRICE_MAX_STAGES = 8;
+// Measured on B200: a block is latency bound (about 2 us from TMA issue to landing under load), so the ring must
+// keep ~48 KB of A per CTA in flight; single-column blocks cannot (half the streaming rate), two-column blocks with
+// six stages can.  Narrow groups shorten the tail of the pass when a CTA gets only a few groups (sharded, m <= 8192).
 constexpr int MIN_CTAS = 2;   // resident CTAs per SM the persistent kernel is compiled for
 constexpr int MAXR = 8;       // ranks (GPUs) of one NVSwitch box
 
@@ -107,6 +112,7 @@ struct Dev {
 	long long row0, ldb;
 	long long col0, nsl;
 	long long k0, k1;                 // share of the unit (slack) columns priced on this rank
+	int price_nc;                     // pricing group width: 4, or 2 when a CTA would get only a few groups
 	long long colstart[MAXR + 1], rowstart[MAXR + 1];
 	unsigned long long* prof;         // optional phase stamps (globaltimer ns), NSTAMP per iteration of a launch
 	long long prof_cap;               // iterations the buffer holds (0 = profiling off)
@@ -205,8 +211,6 @@ struct Smem {
 	long long red_c[NWARP];
 	double wsum[2][PRICE_NC][NWARP];  // pricing: warp sums, double buffered
 	double dsum[2][NWARP];            // O(m) dots
-	double stage[2][CHUNK];           // update_ftran: row_q chunk, a_p chunk (as T)
-	double comb[NWARP][32][4];        // update_ftran: cross-warp combine (WC > 1)
 	double bc_v;                      // broadcasts
 	long long bc_i;
 	long long bc_c;
@@ -216,10 +220,10 @@ struct Smem {
 	long long xi[MAXR];
 	long long xc[MAXR];
 	// pricing ring: TMA bulk copies land in dynamic shared memory, one mbarrier pair per stage
-	unsigned long long full[PRICE_STAGES];
-	unsigned long long empty[PRICE_STAGES];
-	long long ring_group[PRICE_STAGES];   // column group held by the stage, -1 = end of stream
-	int ring_rb[PRICE_STAGES];            // row block of that group
+	unsigned long long full[PRICE_MAX_STAGES];
+	unsigned long long empty[PRICE_MAX_STAGES];
+	long long ring_group[PRICE_MAX_STAGES];   // column group held by the stage, -1 = end of stream
+	int ring_rb[PRICE_MAX_STAGES];            // row block of that group
 };
 
 // ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX)
@@ -255,6 +259,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void fence_proxy_async_global() {
 	asm volatile("fence.proxy.async.global;" ::: "memory");
 }
+// all state spaces: also orders earlier generic-proxy use of the ring's shared memory (it doubles as the
+// update+FTRAN staging area) with the TMA writes that follow
+__device__ __forceinline__ void fence_proxy_async_all() {
+	asm volatile("fence.proxy.async;" ::: "memory");
+}
 // global -> shared bulk copy (TMA, 1-D): completes `bytes` transaction bytes on `bar`; 16-byte aligned everything
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -277,16 +286,19 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
 struct Ring {
 	int stage;
 	unsigned phase;
-	__device__ __forceinline__ void advance() { if (++stage == PRICE_STAGES) { stage = 0; phase ^= 1u; } }
+	int nstages;
+	__device__ __forceinline__ void advance() { if (++stage == nstages) { stage = 0; phase ^= 1u; } }
 };
 
-__device__ __forceinline__ void ring_init(Smem& sh, Ring& cons, Ring& prod) {
+__device__ __forceinline__ void ring_init(Smem& sh, Ring& cons, Ring& prod, int price_nc) {
 	if (threadIdx.x == 0) {
-		for (int s = 0; s < PRICE_STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NWARP); }
+		for (int s = 0; s < PRICE_MAX_STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NWARP); }
 		mbar_fence_init();
 	}
 	cons.stage = prod.stage = 0;
 	cons.phase = prod.phase = 0;
+	const int ns = DYN_SMEM_BYTES / ((price_nc + 1) * PRICE_UNIT);
+	cons.nstages = prod.nstages = ns < PRICE_MAX_STAGES ? ns : PRICE_MAX_STAGES;
 	__syncthreads();
 }
 
@@ -375,13 +387,13 @@ __device__ __forceinline__ long long reduce_counts(const long long* cnt, int n, 
 // e_j = y.A_j - c_j for the ns dense columns, e_j = y_k - c_j for the unit columns, fused
 // with the argmin.  Replaces cublasSgemm(M=1) + cub::DeviceReduce::ArgMin (v4:289-294).
 //
-// A is streamed through a PRICE_STAGES-deep shared-memory ring by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx): one block = PRICE_NC columns x RB rows, RB = NT
+// A is streamed through a shared-memory ring (4 or 6 stages) by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx): one block = y + price_nc columns x RB rows, RB = NT
 // 16-byte vectors, i.e. one row step of the whole CTA.  Thread 0 is the producer and runs
-// PRICE_STAGES-1 blocks ahead of the consumers (all NT threads, itself included), across
+// nstages-1 blocks ahead of the consumers (all NT threads, itself included), across
 // column-group boundaries, so HBM requests never drain while a group is being reduced.
 // Column groups are handed out dynamically: the first one is the CTA's index, the others
-// come from a ticket counter, which evens out slow and fast SMs.  Groups are PRICE_NC columns
+// come from a ticket counter, which evens out slow and fast SMs.  Groups are price_nc columns
 // wide; a ragged remainder goes one column at a time.
 // The summation order of a column does not depend on any of this (see the file header).
 template <typename T>
@@ -391,9 +403,10 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	constexpr int RB = NT * VN;               // rows per block
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const long long ld = d.ld;
-	const long long ntail0 = d.nsl < (long long)PRICE_TAIL * nparts ? d.nsl : (long long)PRICE_TAIL * nparts;
-	const long long nquad = (d.nsl - ntail0) / PRICE_NC;          // full-width groups
-	const long long ngroups = nquad + (d.nsl - nquad * PRICE_NC);  // + single columns
+	const int NCW = d.price_nc;                                  // group width (2 or 4)
+	const int stage_bytes = (NCW + 1) * PRICE_UNIT;
+	const long long nquad = d.nsl / NCW;                         // full-width groups
+	const long long ngroups = nquad + (d.nsl - nquad * NCW);     // + single columns
 	const int nrb = (int)((ld + RB - 1) / RB);
 
 	double best_v = CUDART_INF;
@@ -414,24 +427,25 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 			if (prb == 0) pnext = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // used nrb blocks later
 			const long long r0 = (long long)prb * RB;
 			const unsigned colbytes = (unsigned)((ld - r0 < RB ? ld - r0 : RB) * (long long)sizeof(T));
-			const int nc = pg < nquad ? PRICE_NC : 1;
-			const long long c0 = pg < nquad ? pg * PRICE_NC : nquad * PRICE_NC + (pg - nquad);
+			const int nc = pg < nquad ? NCW : 1;
+			const long long c0 = pg < nquad ? pg * NCW : nquad * NCW + (pg - nquad);
 			sh.ring_group[prod.stage] = pg;
 			sh.ring_rb[prod.stage] = prb;
 			mbar_arrive_expect_tx(&sh.full[prod.stage], (unsigned)(nc + 1) * colbytes);
-			unsigned char* dst = ringbuf + prod.stage * PRICE_STAGE_BYTES;
+			unsigned char* dst = ringbuf + prod.stage * stage_bytes;
 			tma_load_1d(dst, d.y + r0, colbytes, &sh.full[prod.stage]);
 #pragma unroll
 			for (int k = 0; k < PRICE_NC; ++k)
 				if (k < nc)
-					tma_load_1d_hint(dst + (k + 1) * (NT * 16), d.A + (c0 + k) * ld + r0, colbytes, &sh.full[prod.stage], pol_stream);
+					tma_load_1d_hint(dst + (k + 1) * PRICE_UNIT, d.A + (c0 + k) * ld + r0, colbytes, &sh.full[prod.stage], pol_stream);
 			if (++prb == nrb) { prb = 0; pg = pnext; }
 		}
 		prod.advance();
 	};
+	__syncthreads();
 	if (tid == 0) {
-		fence_proxy_async_global();
-		for (int k = 0; k < PRICE_STAGES - 1 && !pend; ++k) produce();
+		fence_proxy_async_all();
+		for (int k = 0; k < prod.nstages - 1 && !pend; ++k) produce();
 	}
 
 	// ---- consumers
@@ -442,7 +456,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 		const bool act = (long long)crb * RB + (long long)tid * VN < ld;
 		mbar_wait(&sh.full[cons.stage], cons.phase);
 		const long long g = sh.ring_group[cons.stage];
-		const int nc = g < nquad ? PRICE_NC : 1;
+		const int nc = g < nquad ? NCW : 1;
 		if (g >= 0) {
 			if (crb == 0) {
 #pragma unroll
@@ -451,12 +465,12 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 					for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
 			}
 			if (act) {
-				const unsigned char* src = ringbuf + cons.stage * PRICE_STAGE_BYTES + tid * 16;
+				const unsigned char* src = ringbuf + cons.stage * stage_bytes + tid * 16;
 				const V yv = *reinterpret_cast<const V*>(src);
 #pragma unroll
 				for (int k = 0; k < PRICE_NC; ++k) {
 					if (k < nc) {
-						const V av = *reinterpret_cast<const V*>(src + (k + 1) * (NT * 16));
+						const V av = *reinterpret_cast<const V*>(src + (k + 1) * PRICE_UNIT);
 #pragma unroll
 						for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(Mem<T>::get(av, v), Mem<T>::get(yv, v), acc[k][v]);
 					}
@@ -484,7 +498,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 				T s = (T)sh.wsum[buf][tid][0];
 #pragma unroll
 				for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
-				const long long c0 = g < nquad ? g * PRICE_NC : nquad * PRICE_NC + (g - nquad);
+				const long long c0 = g < nquad ? g * NCW : nquad * NCW + (g - nquad);
 				const long long j = d.col0 + c0 + tid;               // global column index
 				const double e = (double)(s - d.c[j]);
 				if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
@@ -514,7 +528,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 // WR*32*VN rows x CHUNK columns.  row_q[chunk] and a_p[chunk] are staged in
 // shared memory.  alpha_part[chunk][row] receives the chunk partial.
 template <typename T, int WC, bool UPDATE, bool FTRAN>
-__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, long long uk, bool reverse, int part, int nparts) {
+__device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn, const T* acol, long long uk, bool reverse, int part, int nparts) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
@@ -529,8 +543,10 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, lon
 	const long long ld = d.ldb, m = d.m;   // local row block
 	const long long ntr = (ld + TR - 1) / TR;
 	const long long ntiles = ntr * d.nchunk;
-	T* stage_rq = reinterpret_cast<T*>(sh.stage[0]);
-	T* stage_a = reinterpret_cast<T*>(sh.stage[1]);
+	// staging area in dynamic shared memory (aliases the idle pricing ring): row_q chunk, a_p chunk, combine
+	T* stage_rq = reinterpret_cast<T*>(dyn);
+	T* stage_a = reinterpret_cast<T*>(dyn + CHUNK * 8);
+	double (*comb)[32][4] = reinterpret_cast<double (*)[32][4]>(dyn + 2 * CHUNK * 8);
 	const bool unit = acol == nullptr;     // entering column is the unit vector e_uk
 
 	// tiles are handed out dynamically: the first one is the CTA's index, the others come from a
@@ -634,14 +650,14 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, const T* acol, lon
 			} else {
 				// continue the same pairwise tree across the WC warps that share these rows
 #pragma unroll
-				for (int v = 0; v < VN; ++v) sh.comb[warp][lane][v] = (double)wpart[v];
+				for (int v = 0; v < VN; ++v) comb[warp][lane][v] = (double)wpart[v];
 				__syncthreads();
 				if (wc == 0 && active) {
 					T t[WC][VN];
 #pragma unroll
 					for (int c = 0; c < WC; ++c)
 #pragma unroll
-						for (int v = 0; v < VN; ++v) t[c][v] = (T)sh.comb[c * WR + wr][lane][v];
+						for (int v = 0; v < VN; ++v) t[c][v] = (T)comb[c * WR + wr][lane][v];
 #pragma unroll
 					for (int w = 1; w < WC; w <<= 1)
 #pragma unroll
@@ -764,9 +780,15 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 	__syncthreads();
 	if (tid < 2) {
 		T a = T(0);
-#pragma unroll 8
 		const T* part = tid == 0 ? d.dpart0 : d.dpart + d.nslice;
-		for (int s = 0; s < d.nslice; ++s) a = a + __ldcg(part + s);
+		for (int s0 = 0; s0 < d.nslice; s0 += 32) {      // loads of 32 slices together, adds left to right
+			T v[32];
+#pragma unroll
+			for (int u = 0; u < 32; ++u) v[u] = s0 + u < d.nslice ? __ldcg(part + s0 + u) : T(0);
+#pragma unroll
+			for (int u = 0; u < 32; ++u)
+				if (s0 + u < d.nslice) a = a + v[u];
+		}
 		if (tid == 1) a += d.c[p] - (T)__ldcg(&d.ctl->c_b_q);
 		sh.bc_s[tid] = (double)a;
 	}
@@ -810,7 +832,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
-	ring_init(sh, rcons, rprod);
+	ring_init(sh, rcons, rprod, d.price_nc);
 	Ctl* ctl = d.ctl;
 	const int G = gridDim.x, me = blockIdx.x;
 	unsigned long long epoch = 0;
@@ -836,8 +858,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 
 		// ---- pending rank-1 update fused with the FTRAN of column p
 		const T* acol = p < d.ns ? d.A + p * d.ld : nullptr;
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, acol, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, acol, p - d.ns, pivots & 1, me, G);
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
 		pending = 0;
 		stamp(d, it - it0, 3);
 		grid_barrier(ctl, epoch);
@@ -1092,7 +1114,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
-	ring_init(sh, rcons, rprod);
+	ring_init(sh, rcons, rprod, d.price_nc);
 	Ctl* ctl = d.ctl;
 	const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
 	unsigned long long epoch = 0;
@@ -1129,8 +1151,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 			if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
 		}
 		stamp(d, it - it0, 3);
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
 		pending = 0;
 		stamp(d, it - it0, 4);
 		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
@@ -1186,7 +1208,7 @@ __global__ void __launch_bounds__(NT) k_price(Dev<T> d) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
-	ring_init(sh, rcons, rprod);
+	ring_init(sh, rcons, rprod, d.price_nc);
 	price_phase<T>(d, sh, ringbuf, rcons, rprod, blockIdx.x, gridDim.x);
 }
 
@@ -1207,7 +1229,8 @@ __global__ void __launch_bounds__(NT) k_pick(Dev<T> d, int ncand, int kind) {
 template <typename T, int WC, bool UPDATE, bool FTRAN>
 __global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p, int reverse) {
 	__shared__ Smem sh;
-	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
+	extern __shared__ __align__(128) unsigned char dyn[];
+	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, dyn, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
 }
 
 template <typename T>

@@ -42,16 +42,18 @@ def run(args, wl, seed, eps):
         torch.cuda.synchronize()
         return a.elapsed_time(b_), r, r["kernel_launches"] - l0
 
-    for _ in range(args.warmup):
-        window()
     ms, piv, launches = [], 0, 0
     from bench import ClockSampler          # same sampler as the single-GPU arm
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            window()
+        clk.mark_start()
         for _ in range(args.steps):
             t, r, l = window()
             ms.append(t)
             piv += r["pivots"]
             launches += l
+        clk.mark_end()
     t_ms = torch.tensor(ms, dtype=torch.float64, device="cuda")
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)                 # device time, max over ranks
     total_ms = float(t_ms.sum().item())
