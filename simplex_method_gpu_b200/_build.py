@@ -38,13 +38,16 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libb200lp.so and bin/solver.out when sources are newer than the binaries."""
-    lib_src = [os.path.join(_CSRC, f) for f in ("engine.cu", "kernels.cuh")] + [os.path.join(_ROOT, "include", "b200lp.h")]
+    lib_src = [os.path.join(_CSRC, f) for f in ("engine.cu", "kernels.cuh", "lp_io.cpp")] + \
+              [os.path.join(_ROOT, "include", h) for h in ("b200lp.h", "b200lp_io.h")]
     if force or _stale(LIB_PATH, lib_src):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB_PATH, os.path.join(_CSRC, "engine.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB_PATH, os.path.join(_CSRC, "engine.cu"),
+               os.path.join(_CSRC, "lp_io.cpp")]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True, capture_output=not verbose)
-    cli_src = [os.path.join(_CSRC, "solver_main.cpp"), os.path.join(_ROOT, "include", "b200lp.h")]
+    cli_src = [os.path.join(_CSRC, "solver_main.cpp"), os.path.join(_ROOT, "include", "b200lp.h"),
+               os.path.join(_ROOT, "include", "b200lp_io.h")]
     if os.path.exists(cli_src[0]) and (force or _stale(CLI_PATH, cli_src + [LIB_PATH])):
         os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
         cmd = [_nvcc(), "-O2", "-std=c++17", "-o", CLI_PATH, cli_src[0], "-I", os.path.join(_ROOT, "include"),

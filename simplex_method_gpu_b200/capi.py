@@ -22,6 +22,8 @@ EXPORTS = [
     "b200lp_create_sharded", "b200lp_ipc_handle_bytes", "b200lp_ipc_export", "b200lp_ipc_import", "b200lp_shard_rows",
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
     "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile",
+    # include/b200lp_io.h
+    "b200lp_read_lp", "b200lp_write_lp_text", "b200lp_write_lp_binary", "b200lp_free_problem",
 ]
 
 
@@ -35,6 +37,12 @@ class Result(C.Structure):
     _fields_ = [("status", C.c_int32), ("reserved", C.c_int32), ("iterations", C.c_int64), ("pivots", C.c_int64),
                 ("z", C.c_double), ("min_reduced_cost", C.c_double), ("ms_upload", C.c_double),
                 ("ms_solve", C.c_double), ("ms_download", C.c_double), ("kernel_launches", C.c_int64)]
+
+
+class Problem(C.Structure):
+    """b200lp_problem (include/b200lp_io.h)."""
+    _fields_ = [("dtype", C.c_int32), ("reserved", C.c_int32), ("m", C.c_int64), ("n", C.c_int64),
+                ("A", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p)]
 
 
 class B200LPError(RuntimeError):
@@ -91,6 +99,10 @@ def lib() -> C.CDLL:
         "b200lp_profile_stamps": (C.c_int, []),
         "b200lp_profile_names": (C.c_char_p, []),
         "b200lp_download_profile": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
+        "b200lp_read_lp": (C.c_int, [C.c_char_p, i32, i32, C.POINTER(Problem)]),
+        "b200lp_write_lp_text": (C.c_int, [C.c_char_p, C.POINTER(Problem)]),
+        "b200lp_write_lp_binary": (C.c_int, [C.c_char_p, C.POINTER(Problem)]),
+        "b200lp_free_problem": (None, [C.POINTER(Problem)]),
         "b200lp_last_error": (C.c_char_p, []),
         "b200lp_version": (C.c_char_p, []),
     }

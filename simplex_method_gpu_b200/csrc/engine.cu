@@ -729,6 +729,9 @@ static void lpgen_host(T* A, T* b, T* c, int64_t m, int64_t n, int64_t col0, int
 
 extern "C" {
 
+// used by the other translation units of the library (lp_io.cpp); not part of the public ABI
+int b200lp_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
 int b200lp_lpgen_dense_host(int32_t dtype, void* A_cols, void* b, void* c, int64_t m, int64_t n,
 		int64_t col0, int64_t ncols, uint64_t seed) {
 	if (m <= 0 || n < m || col0 < 0 || ncols < 0 || col0 + ncols > n) return fail(B200LP_ERR_ARG, "lpgen: bad shape");

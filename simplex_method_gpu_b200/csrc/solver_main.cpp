@@ -1,11 +1,12 @@
 // CLI with the driver contract of the reference's main() (src/v4_cub_reduction.cu:384-474):
-//   solver.out <lp.txt> [--f64] [--eps E] [--max-iter N] [--device D]
-// Same input text format (v4:401-420), same stdout: one "# Iteration k" line per
+//   solver.out <lp.txt | lp.b200lp> [--f64] [--eps E] [--max-iter N] [--device D]
+// Same input text format (v4:401-420; parsed by b200lp_read_lp, which also accepts the binary twin), same stdout: one "# Iteration k" line per
 // iteration (v4:287), the result block (v4:426-445) and the timing block
 // (v4:456-471, same labels and number format).  Defaults reproduce the reference's
 // compile-time constants: real = float, EPS = 1e-4, MAX_ITER = 5 (v4:12, 18-19).
 // All numerics run in libb200lp.so through the C ABI.
 #include "b200lp.h"
+#include "b200lp_io.h"
 
 #include <chrono>
 #include <cstdio>
@@ -28,71 +29,30 @@ static void print_time(const char* label, double s) {
 	std::cout << std::fixed << std::setprecision(2) << std::setw(6) << s << '\n';
 }
 
-struct Tokens {
-	std::vector<char> buf;
-	char* cur = nullptr;
-	bool load(const char* path) {
-		FILE* f = std::fopen(path, "rb");
-		if (!f) return false;
-		std::fseek(f, 0, SEEK_END);
-		long sz = std::ftell(f);
-		std::fseek(f, 0, SEEK_SET);
-		buf.resize((size_t)sz + 1);
-		size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
-		std::fclose(f);
-		buf[got] = 0;
-		cur = buf.data();
-		return true;
-	}
-	bool next_long(long& v) {
-		char* end;
-		v = std::strtol(cur, &end, 10);
-		if (end == cur) return false;
-		cur = end;
-		return true;
-	}
-	bool next_double(double& v) {
-		char* end;
-		v = std::strtod(cur, &end);
-		if (end == cur) return false;
-		cur = end;
-		return true;
-	}
-};
-
-// row-major text -> column-major storage (v4:94-104)
 template <typename T>
-static bool load_matrix(Tokens& tk, std::vector<T>& a, long rows, long cols, const char* name) {
-	for (long i = 0; i < rows; ++i)
-		for (long j = 0; j < cols; ++j) {
-			double v;
-			if (!tk.next_double(v)) {
-				std::cerr << "Failed to read (" << i << "," << j << ") for " << name << "\n";
-				return false;
-			}
-			a[(size_t)i + (size_t)j * rows] = (T)v;
-		}
-	return true;
-}
-
-template <typename T>
-static int run(Tokens& tk, long m, long n, b200lp_options opt, Clock::time_point t_start) {
+static int run(const char* path, b200lp_options opt, Clock::time_point t_start) {
+	// the reference allocates its pinned host arrays first and then parses into them (v4:407-420);
+	// here the reader does both, so "Host alloc" is the output arrays only
 	auto t_host_alloc = Clock::now();
-	std::vector<T> A((size_t)m * n), b((size_t)m), c((size_t)n), x_b((size_t)m);
-	std::vector<int32_t> b_ixs((size_t)m);
-
 	auto t_read = Clock::now();
-	if (!load_matrix(tk, A, m, n, "A") || !load_matrix(tk, b, m, 1, "b") || !load_matrix(tk, c, 1, n, "c"))
-		return EXIT_FAILURE;
+	b200lp_problem lp;
+	if (b200lp_read_lp(path, sizeof(T) == 8 ? B200LP_F64 : B200LP_F32, 1, &lp) != B200LP_OK) {
+		std::cerr << b200lp_last_error() << "\n";
+		return 1;                                    // v4:398, 404; a short file exits with EXIT_FAILURE = 1 too (v4:100)
+	}
+	const long m = (long)lp.m, n = (long)lp.n;
+	const T *A = (const T*)lp.A, *b = (const T*)lp.b, *c = (const T*)lp.c;
+	std::vector<T> x_b((size_t)m);
+	std::vector<int32_t> b_ixs((size_t)m);
 
 	auto t_solve = Clock::now();
 	b200lp_result r;
 	int rc;
 	if (sizeof(T) == 8)
-		rc = b200lp_solve_f64((const double*)A.data(), (const double*)b.data(), (const double*)c.data(), m, n, &opt,
+		rc = b200lp_solve_f64((const double*)A, (const double*)b, (const double*)c, m, n, &opt,
 				(double*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
 	else
-		rc = b200lp_solve_f32((const float*)A.data(), (const float*)b.data(), (const float*)c.data(), m, n, &opt,
+		rc = b200lp_solve_f32((const float*)A, (const float*)b, (const float*)c, m, n, &opt,
 				(float*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
 	if (rc != B200LP_OK) {
 		std::cerr << "b200lp failed (" << rc << "): " << b200lp_last_error() << "\n";
@@ -113,7 +73,7 @@ static int run(Tokens& tk, long m, long n, b200lp_options opt, Clock::time_point
 	std::cout << '\n';
 
 	auto t_free = Clock::now();
-	A.clear(); A.shrink_to_fit();
+	b200lp_free_problem(&lp);
 	auto t_end = Clock::now();
 
 	// the pivot loop is one fused kernel, so the reference's per-phase host timers
@@ -161,15 +121,5 @@ int main(int argc, char* argv[]) {
 		}
 	}
 
-	Tokens tk;
-	if (!tk.load(argv[1])) {
-		std::cerr << "Could not open " << argv[1] << ".\n";
-		return 1;
-	}
-	long m = 0, n = 0;
-	if (!tk.next_long(m) || !tk.next_long(n) || m > n || m <= 0) {
-		std::cerr << "Either failed to read m and n, or m > n.\n";
-		return 1;
-	}
-	return f64 ? run<double>(tk, m, n, opt, t_start) : run<float>(tk, m, n, opt, t_start);
+	return f64 ? run<double>(argv[1], opt, t_start) : run<float>(argv[1], opt, t_start);
 }

@@ -283,6 +283,36 @@ def read_lp(path_or_file, dtype=REAL):
     return A, b, c
 
 
+def read_lp_native(path, dtype=REAL):
+    """Same contract as read_lp, through the library's parallel reader (include/b200lp_io.h); also reads
+    the binary twin of the format.  Raises ValueError with the reference's messages (v4:397-404, 99)."""
+    dt = np.dtype(dtype)
+    L = capi.lib()
+    prob = capi.Problem()
+    rc = L.b200lp_read_lp(str(path).encode(), _dtype_code(dt), 0, C.byref(prob))
+    if rc != capi.OK:
+        raise ValueError(L.b200lp_last_error().decode())
+    try:
+        m, n = prob.m, prob.n
+        ct = C.c_double if dt == np.float64 else C.c_float
+        A = np.ctypeslib.as_array(C.cast(prob.A, C.POINTER(ct)), shape=(n, m)).T.copy(order="F")
+        b = np.ctypeslib.as_array(C.cast(prob.b, C.POINTER(ct)), shape=(m,)).copy()
+        c = np.ctypeslib.as_array(C.cast(prob.c, C.POINTER(ct)), shape=(n,)).copy()
+    finally:
+        L.b200lp_free_problem(C.byref(prob))
+    return A, b, c
+
+
+def write_lp_native(path, A, b, c, binary=False):
+    """Write the text format (shortest round-trip decimals) or the binary twin through the library."""
+    A, b, c, m, n, dt = _prep(A, b, c, None)
+    prob = capi.Problem(_dtype_code(dt), 0, m, n, A.ctypes.data, b.ctypes.data, c.ctypes.data)
+    L = capi.lib()
+    fn = L.b200lp_write_lp_binary if binary else L.b200lp_write_lp_text
+    if fn(str(path).encode(), C.byref(prob)) != capi.OK:
+        raise OSError(L.b200lp_last_error().decode())
+
+
 def write_lp(path, A, b, c):
     m, n = A.shape
     with open(path, "w") as f:

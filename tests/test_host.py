@@ -13,11 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def test_library_exports_every_declared_symbol(engine_lib):
     from simplex_method_gpu_b200 import capi
-    with open(os.path.join(ROOT, "include", "b200lp.h")) as f:
-        header = f.read()
+    header = ""
+    for h in ("b200lp.h", "b200lp_io.h"):
+        with open(os.path.join(ROOT, "include", h)) as f:
+            header += f.read()
     declared = set(re.findall(r"\b(b200lp_[a-z0-9_]+)\s*\(", header))
     declared -= {"b200lp_engine"}
-    assert declared, "no prototypes found in include/b200lp.h"
+    assert declared, "no prototypes found in include/*.h"
     for name in sorted(declared):
         assert hasattr(engine_lib, name), f"{name} declared in b200lp.h but not exported"
     assert declared == set(capi.EXPORTS)
@@ -102,3 +104,66 @@ def test_format_result_matches_reference_stdout():
     sol = s.Solution(1234567.0, s.SolveStatus.OptimumFound, np.array([0.1 + 0.2]), np.array([7], np.int32), 1, 0,
                      np.zeros((0, 2), np.int32))
     assert s.format_result(sol) == "# Iteration 1\nOptimum found: 1.23457e+06\n\tx_7 = 0.3\n\n"   # ostream default: 6 sig. digits
+
+
+# ---------------------------------------------------------------- include/b200lp_io.h (host code, runs without a GPU)
+
+def test_native_reader_matches_python_reader_on_the_reference_fixture(engine_lib):
+    import simplex_method_gpu_b200 as s
+    from simplex_method_gpu_b200.solver import read_lp_native
+    path = os.path.join(GOLDEN, "sample.txt")
+    for dt in (np.float32, np.float64):
+        A0, b0, c0 = s.read_lp(path, dtype=dt)
+        A1, b1, c1 = read_lp_native(path, dtype=dt)
+        assert A1.flags.f_contiguous and A1.dtype == dt
+        assert np.array_equal(A0, A1) and np.array_equal(b0, b1) and np.array_equal(c0, c1)
+
+
+def test_native_text_and_binary_round_trip(engine_lib, oracle, tmp_path):
+    from simplex_method_gpu_b200.solver import read_lp_native, write_lp_native
+    A, b, c = oracle.gen_dense(37, 90, 5)
+    A[3, 4], b[2], c[1] = -1.25e-300, 1e300, -0.0          # awkward values must survive the text form
+    txt, binf = str(tmp_path / "lp.txt"), str(tmp_path / "lp.b200lp")
+    write_lp_native(txt, A, b, c)
+    write_lp_native(binf, A, b, c, binary=True)
+    for path in (txt, binf):
+        A1, b1, c1 = read_lp_native(path, dtype=np.float64)
+        assert np.array_equal(A, A1) and np.array_equal(b, b1) and np.array_equal(c, c1), path
+    A32, b32, c32 = read_lp_native(binf, dtype=np.float32)                 # binary of the other dtype is converted
+    assert np.array_equal(A32, A.astype(np.float32)) and np.array_equal(c32, c.astype(np.float32))
+    with open(txt) as f:
+        assert f.readline().split() == ["37", "90"]                           # v4:401 header
+
+
+def test_native_reader_is_parallel_safe_on_a_larger_file(engine_lib, oracle, tmp_path):
+    """Big enough that the reader cuts the text into several per-thread pieces."""
+    from simplex_method_gpu_b200.solver import read_lp_native, write_lp_native
+    A, b, c = oracle.gen_dense(300, 700, 8)
+    path = str(tmp_path / "big.txt")
+    write_lp_native(path, A, b, c)
+    assert os.path.getsize(path) > 1 << 20
+    A1, b1, c1 = read_lp_native(path, dtype=np.float64)
+    assert np.array_equal(A, A1) and np.array_equal(b, b1) and np.array_equal(c, c1)
+    with open(path, "a") as f:
+        f.write("\nOptimum: 12.5 at x0 = 1\n")                            # trailing text is ignored (input/sample.txt:15-16)
+    A2, _, c2 = read_lp_native(path, dtype=np.float64)
+    assert np.array_equal(A, A2) and np.array_equal(c, c2)
+
+
+def test_native_reader_errors_use_the_reference_messages(engine_lib, tmp_path):
+    from simplex_method_gpu_b200.solver import read_lp_native
+    with pytest.raises(ValueError, match=r"Could not open .*nope\.txt\."):        # v4:397
+        read_lp_native(str(tmp_path / "nope.txt"))
+    p = tmp_path / "bad.txt"
+    p.write_text("3 2\n1 2 3 4 5 6\n1 1 1\n1 1\n")
+    with pytest.raises(ValueError, match="Either failed to read m and n, or m > n."):   # v4:403
+        read_lp_native(str(p))
+    p.write_text("2 4\n1 1 1 0\n1 x 0 1\n3 4\n1 1 0 0\n")
+    with pytest.raises(ValueError, match=r"Failed to read \(1,1\) for A"):           # v4:99
+        read_lp_native(str(p))
+    p.write_text("2 4\n1 1 1 0\n1 2 0 1\n3\n")
+    with pytest.raises(ValueError, match=r"Failed to read \(1,0\) for b"):
+        read_lp_native(str(p))
+    p.write_text("2 4\n1 1 1 0\n1 2 0 1\n3 4\n1 1 0\n")
+    with pytest.raises(ValueError, match=r"Failed to read \(0,3\) for c"):
+        read_lp_native(str(p))
