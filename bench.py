@@ -46,6 +46,34 @@ SEED = 1
 EPS = 1e-9
 
 
+def profiled_traffic(workload, pivots_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the persistent kernel from the committed ncu capture
+    (profiles/r01_traffic.json, written by tools/ncu_extract.py), scaled to this launch's pivot count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_per_pivot"] * pivots_per_launch, t
+    except Exception:
+        return None, None
+
+
+def time_to_optimal(name, wl, dev=0):
+    """Whole solve from the slack basis to the optimum on one GPU (the other half of BASELINE.json's metric)."""
+    import simplex_method_gpu_b200 as lp
+    m, n = wl["m"], wl["n"]
+    eng = lp.Engine(m, n, np.float64, eps=EPS, max_iter=1 << 40, device=dev)
+    eng.generate_dense(SEED)
+    eng.run(8)                       # warm-up launch
+    eng.reset()
+    t0 = time.perf_counter()
+    r = eng.run(1 << 40)
+    wall = time.perf_counter() - t0
+    eng.close()
+    return {"workload": f"{name}: dense LP m={m} n={n}, seed {SEED}, slack basis to optimum", "status": int(r["status"]),
+            "pivots": int(r["pivots"]), "iterations": int(r["iterations"]), "z": r["z"],
+            "seconds": r["ms_solve"] * 1e-3, "wall_seconds": wall, "pivots_per_s": r["pivots"] / (r["ms_solve"] * 1e-3)}
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -194,6 +222,7 @@ def run_b200_single(args, wl):
     peak, peak_src = measured_peak_gbs()
     bpp = bytes_per_pivot(m, n)
     achieved = bpp * pivots_timed / (total_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(args.workload, P)
     out = {
         "metric": "pivots/s, dense revised simplex (fp64)", "value": value, "unit": "pivots/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -205,8 +234,8 @@ def run_b200_single(args, wl):
                          "working set fits the 126 MB L2 (L2-resident; roofline fraction may exceed 1)",
                    "parallelism": "1 GPU, persistent cooperative kernel"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_pivot": bpp,
-                     "kernel": "simplex_persistent<double>"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_pivot": bpp,
+                     "bytes_per_launch": bpp * P, "kernel": "simplex_persistent<double>"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e,
         "status_after": status_after, "pivots_timed": int(pivots_timed), "engine_event_ms": internal_ms,
     }
@@ -301,6 +330,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", default="C3", help="comma list of extra single-GPU workloads reported under 'extra'")
+    ap.add_argument("--tto", default="C2,C3", help="comma list of workloads solved to optimality (time-to-optimal), '' = none")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU port")
     ap.add_argument("--ref-pivots", type=int, default=0)
     args = ap.parse_args()
@@ -328,6 +358,11 @@ def main():
             sub.workload, sub.pivots, sub.no_e2e = name, 0, True
             r = run_b200_single(sub, WORKLOADS[name])
             extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "roofline", "config", "clocks", "gpu_launches")}
+        tto = {}
+        for name in [x for x in args.tto.split(",") if x]:
+            tto[name] = time_to_optimal(name, WORKLOADS[name], int(os.environ.get("LOCAL_RANK", "0")))
+        if tto:
+            extra["time_to_optimal"] = tto
         if extra:
             out["extra"] = extra
     if rank == 0 and out is not None:

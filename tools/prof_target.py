@@ -1,0 +1,28 @@
+"""Profiling target (GPU box): L consecutive persistent launches of P pivots each on one dense LP, no reset in
+between, so every launch after the first is steady state (pending rank-1 update, warm TLB).  With --phases the
+same pivots run in one-launch-per-phase mode (k_price / k_update_ftran / k_ratio / k_book1 / k_book2).
+
+    python tools/prof_target.py --lp 32768x65536 --pivots 8 --launches 3
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simplex_method_gpu_b200 as lp  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--lp", default="8192x16384")
+ap.add_argument("--pivots", type=int, default=16)
+ap.add_argument("--launches", type=int, default=3)
+ap.add_argument("--phases", action="store_true")
+a = ap.parse_args()
+m, n = (int(x) for x in a.lp.lower().split("x"))
+e = lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 30, mode=1 if a.phases else 0)
+e.generate_dense(1)
+for k in range(a.launches):
+    r = e.run(a.pivots)
+    print(f"launch {k}: {r['pivots']} pivots total, {r['ms_solve']:.3f} ms, status {int(r['status'])}", flush=True)
+e.close()
