@@ -63,7 +63,8 @@ typedef struct {
 	int32_t profile;      /* > 0: record phase time stamps for the first `profile` iterations of every
 	                         persistent launch (b200lp_download_profile); 0 = off (default) */
 	int32_t price_cols;   /* pricing group width: 0 = auto, else 2 | 4 columns per TMA block */
-	int32_t reserved;
+	int32_t l2_persist_mb; /* pin the head of B^-1 in the persisting part of L2: -1 = off (default), 0 = as much as
+	                          the device allows, else MiB */
 } b200lp_options;
 
 typedef struct {

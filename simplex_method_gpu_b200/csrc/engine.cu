@@ -131,6 +131,28 @@ public:
 			CU(alloc(&d.prof, (size_t)d.prof_cap * NSTAMP));
 		}
 
+		// L2 residency: pin the head of B^-1 in the persisting part of L2 so that it never makes the trip to HBM
+		// (B^-1 is read and rewritten once per pivot; A streams through with evict_first)
+		if (opt.l2_persist_mb >= 0) {
+			int max_persist = 0, max_window = 0;
+			CU(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, opt.device));
+			CU(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, opt.device));
+			size_t want = opt.l2_persist_mb > 0 ? (size_t)opt.l2_persist_mb << 20 : (size_t)max_persist;
+			want = std::min({want, (size_t)max_persist, (size_t)max_window, (size_t)d.ldb * m * sizeof(T)});
+			if (want >= ((size_t)4 << 20) && (size_t)d.ldb * m * sizeof(T) > ((size_t)64 << 20)) {
+				CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+				cudaStreamAttrValue av;
+				std::memset(&av, 0, sizeof(av));
+				av.accessPolicyWindow.base_ptr = d.B;
+				av.accessPolicyWindow.num_bytes = want;
+				av.accessPolicyWindow.hitRatio = 1.0f;
+				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				CU(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+				l2_persist_bytes = want;
+			}
+		}
+
 		// persistent grid: co-resident CTAs only (cooperative launch)
 		// the pricing ring lives in dynamic shared memory (above the 48 KB default limit)
 		for (const void* fn : {(const void*)simplex_persistent<T, 1>, (const void*)simplex_persistent<T, 2>,
@@ -172,12 +194,19 @@ public:
 	int upload(const void* Av, const void* bv, const void* cv) override {
 		const T* A = static_cast<const T*>(Av);
 		const long long m = d.m, n = d.n;
-		// Is the last m x m block the identity the reference assumes (v4:272)?  If so
-		// those columns are priced and FTRAN'd as unit vectors and never stored.
-		bool slack_ok = true;
-		if (opt.check_slack) slack_ok = host_is_identity(A + (size_t)(n - m) * m, m);
 		CU(cudaSetDevice(opt.device));
-		CU(set_columns(slack_ok ? n - m : n));
+		// Is the last m x m block the identity the reference assumes (v4:272)?  If so those columns are
+		// priced and FTRAN'd as unit vectors and never stored.  The check reads m*m host elements (8.6 GB at
+		// m = 32768), so the structural columns are put on the wire first and the check runs on the host
+		// threads while the DMA engine works (pinned memory; a pageable copy simply finishes first).
+		if (opt.check_slack && n > m) {
+			CU(set_columns(n - m));
+			int rc = enqueue_block(A + (size_t)d.col0 * m, bv, cv);
+			if (rc) return rc;
+			if (host_is_identity(A + (size_t)(n - m) * m, m)) return finish_upload();
+			CU(cudaStreamSynchronize(stream));       // rare: the block is data, store and price all n columns
+		}
+		CU(set_columns(opt.check_slack ? n : n - m));
 		return upload_block(A + (size_t)d.col0 * m, bv, cv);
 	}
 
@@ -192,6 +221,12 @@ public:
 	}
 
 	int upload_block(const void* Av, const void* bv, const void* cv) {
+		int rc = enqueue_block(Av, bv, cv);
+		return rc ? rc : finish_upload();
+	}
+
+	// H2D of this rank's column block, b and c: enqueued on the engine's stream, not waited for
+	int enqueue_block(const void* Av, const void* bv, const void* cv) {
 		const T* A = static_cast<const T*>(Av);          // first column of this rank's block
 		const T* b = static_cast<const T*>(bv);
 		const T* c = static_cast<const T*>(cv);
@@ -208,6 +243,11 @@ public:
 			launches++;
 		}
 		CU(cudaEventRecord(ev1, stream));
+		return B200LP_OK;
+	}
+
+	// slack-basis initial state, then wait for the copies
+	int finish_upload() {
 		have_data = true;
 		int rc = reset();
 		if (rc) return rc;
@@ -518,6 +558,7 @@ private:
 
 	void release() {
 		if (stream) cudaStreamSynchronize(stream);
+		if (l2_persist_bytes) cudaCtxResetPersistingL2Cache();
 		for (void* p : opened) cudaIpcCloseMemHandle(p);
 		opened.clear();
 		for (void* p : owned) cudaFree(p);
@@ -643,6 +684,7 @@ private:
 	bool have_data = false, in_flight = false;
 	int64_t launches = 0;
 	long long prof_iter0 = 0;
+	size_t l2_persist_bytes = 0;
 };
 
 template <typename T>
@@ -748,6 +790,7 @@ void b200lp_default_options(b200lp_options* opt) {
 	opt->max_iter = 5;    // v4:19
 	opt->device = 0;
 	opt->check_slack = 1;
+	opt->l2_persist_mb = -1;
 }
 
 int b200lp_solve_f64(const double* A, const double* b, const double* c, int64_t m, int64_t n,

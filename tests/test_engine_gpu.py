@@ -68,6 +68,27 @@ def test_cli_stdout_matches_reference_contract(lp):
     assert r.returncode == 1 and "Could not open /nonexistent." in r.stderr           # v4:396-399
 
 
+def test_cli_reads_the_binary_twin_and_reports_parse_errors(lp, tmp_path):
+    """bin/solver.out goes through b200lp_read_lp: binary LP files give the same stdout, short files the reference's message."""
+    from simplex_method_gpu_b200.solver import write_lp_native
+    exe = os.path.join(ROOT, "bin", "solver.out")
+    A, b, c = lp.read_lp(os.path.join(GOLDEN, "sample.txt"), dtype=np.float32)
+    binf = str(tmp_path / "sample.b200lp")
+    write_lp_native(binf, A, b, c, binary=True)
+    head = "# Iteration 1\n# Iteration 2\n# Iteration 3\nOptimum found: 9\n\tx_1 = 3\n\tx_0 = 1\n\n"
+    for extra in ([], ["--f64"]):
+        out = subprocess.run([exe, binf] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and out.stdout.startswith(head), out.stderr
+    short = tmp_path / "short.txt"
+    short.write_text("2 4\n1 1 1 0\n2 1 0\n")
+    r = subprocess.run([exe, str(short)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "Failed to read (1,3) for A" in r.stderr                 # v4:99-100
+    bad = tmp_path / "bad.txt"
+    bad.write_text("5 4\n")
+    r = subprocess.run([exe, str(bad)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "Either failed to read m and n, or m > n." in r.stderr   # v4:403
+
+
 def test_max_iter_and_unbounded(lp, oracle):
     A, b, c = lp.read_lp(os.path.join(GOLDEN, "sample.txt"), dtype=np.float64)
     for k in (1, 2, 3):
