@@ -389,7 +389,7 @@ __device__ __forceinline__ long long reduce_counts(const long long* cnt, int n, 
 //
 // A is streamed through a shared-memory ring (4 or 6 stages) by TMA bulk copies
 // (cp.async.bulk + mbarrier complete_tx): one block = y + price_nc columns x RB rows, RB = NT
-// 16-byte vectors, i.e. one row step of the whole CTA.  Thread 0 is the producer and runs
+// 16-byte vectors, i.e. one row step of the whole CTA.  Warp 0 is the producer and runs
 // nstages-1 blocks ahead of the consumers (all NT threads, itself included), across
 // column-group boundaries, so HBM requests never drain while a group is being reduced.
 // Column groups are handed out dynamically: the first one is the CTA's index, the others
@@ -412,7 +412,9 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 
-	// ---- producer cursor (meaningful in thread 0 only)
+	// ---- producer: warp 0, all lanes in step (same cursor in every lane).  One thread issuing a block alone
+	// needs ~0.3 us of dependent scalar work per block, more than a 2-column block takes to stream; spread over
+	// the lanes (lane 0: barrier bookkeeping, lane 1: y, lanes 2..: one column each) it is a third of that.
 	const unsigned long long pol_stream = l2_policy_evict_first();   // A is read once per pivot
 	long long pg = part, pnext = ngroups;
 	int prb = 0;
@@ -420,30 +422,35 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	auto produce = [&]() {
 		mbar_wait(&sh.empty[prod.stage], prod.phase ^ 1u);       // consumers have released the stage
 		if (pg >= ngroups) {
-			sh.ring_group[prod.stage] = -1;                        // end of this CTA's stream
-			mbar_arrive(&sh.full[prod.stage]);
+			if (lane == 0) {
+				sh.ring_group[prod.stage] = -1;                    // end of this CTA's stream
+				mbar_arrive(&sh.full[prod.stage]);
+			}
 			pend = true;
 		} else {
-			if (prb == 0) pnext = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // used nrb blocks later
+			if (prb == 0 && lane == 0) pnext = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // used nrb blocks later
 			const long long r0 = (long long)prb * RB;
 			const unsigned colbytes = (unsigned)((ld - r0 < RB ? ld - r0 : RB) * (long long)sizeof(T));
 			const int nc = pg < nquad ? NCW : 1;
 			const long long c0 = pg < nquad ? pg * NCW : nquad * NCW + (pg - nquad);
-			sh.ring_group[prod.stage] = pg;
-			sh.ring_rb[prod.stage] = prb;
-			mbar_arrive_expect_tx(&sh.full[prod.stage], (unsigned)(nc + 1) * colbytes);
 			unsigned char* dst = ringbuf + prod.stage * stage_bytes;
-			tma_load_1d(dst, d.y + r0, colbytes, &sh.full[prod.stage]);
-#pragma unroll
-			for (int k = 0; k < PRICE_NC; ++k)
-				if (k < nc)
-					tma_load_1d_hint(dst + (k + 1) * PRICE_UNIT, d.A + (c0 + k) * ld + r0, colbytes, &sh.full[prod.stage], pol_stream);
-			if (++prb == nrb) { prb = 0; pg = pnext; }
+			if (lane == 0) {
+				sh.ring_group[prod.stage] = pg;
+				sh.ring_rb[prod.stage] = prb;
+				// the phase cannot complete before this arrival, whatever the order of the copies' complete_tx
+				mbar_arrive_expect_tx(&sh.full[prod.stage], (unsigned)(nc + 1) * colbytes);
+			} else if (lane == 1) {
+				tma_load_1d(dst, d.y + r0, colbytes, &sh.full[prod.stage]);
+			} else if (lane < nc + 2) {
+				const int k = lane - 2;
+				tma_load_1d_hint(dst + (k + 1) * PRICE_UNIT, d.A + (c0 + k) * ld + r0, colbytes, &sh.full[prod.stage], pol_stream);
+			}
+			if (++prb == nrb) { prb = 0; pg = __shfl_sync(0xffffffffu, pnext, 0); }
 		}
 		prod.advance();
 	};
 	__syncthreads();
-	if (tid == 0) {
+	if (warp == 0) {
 		fence_proxy_async_all();
 		for (int k = 0; k < prod.nstages - 1 && !pend; ++k) produce();
 	}
@@ -452,7 +459,7 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	T acc[PRICE_NC][VN];
 	int crb = 0, buf = 0;
 	while (true) {
-		if (tid == 0 && !pend) produce();
+		if (warp == 0 && !pend) produce();
 		const bool act = (long long)crb * RB + (long long)tid * VN < ld;
 		mbar_wait(&sh.full[cons.stage], cons.phase);
 		const long long g = sh.ring_group[cons.stage];

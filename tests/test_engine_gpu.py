@@ -146,7 +146,19 @@ def test_klee_minty_exact(lp, oracle, d):
     assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs)
 
 
-@pytest.mark.parametrize("k", [8, 16, 32])
+def test_klee_minty_20_full_config(lp, oracle):
+    """BASELINE config 5a at full size: 2^20 - 1 pivots, optimum 5^20, every pivot identical to the oracle's."""
+    A, b, c = oracle.gen_klee_minty(20)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 22)
+    assert sol.status == lp.SolveStatus.OptimumFound and sol.pivots == 2 ** 20 - 1 and sol.z == 5.0 ** 20
+    assert sol.kernel_launches <= 4                                   # one persistent launch, not one per pivot
+    ref = oracle.solve(A, b, c, eps=1e-4, max_iter=1 << 22)
+    assert ref.pivots == sol.pivots and ref.z == sol.z
+    assert np.array_equal(sol.trace[:, 0], ref.trace_p) and np.array_equal(sol.trace[:, 1], ref.trace_q)
+    assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs)
+
+
+@pytest.mark.parametrize("k", [8, 16, 32, 64])
 def test_assignment_exact_with_ties(lp, oracle, k):
     A, b, c, w = oracle.gen_assignment(k, 1)
     ref = oracle.solve(A, b, c, eps=1e-4, max_iter=1 << 20)
@@ -280,3 +292,67 @@ def test_device_generator_matches_oracle_generator(lp, oracle):
         x_b, b_ixs, _ = e.download()
         assert r["pivots"] == host.pivots and r["z"] == host.z
         assert np.array_equal(x_b, host.x_b) and np.array_equal(b_ixs, host.b_ixs)
+
+
+# ---------------------------------------------------------------- BASELINE's full sizes: size-independent properties
+
+def _column(m, n, j, seed=1):
+    """Column j of the synthetic dense LP [A_s, I] without materialising the matrix."""
+    from simplex_method_gpu_b200.solver import lpgen_dense_into
+    col = np.empty(m, np.float64)
+    lpgen_dense_into(col.ctypes.data, 0, 0, m, n, j, 1, seed)
+    return col
+
+
+@pytest.mark.parametrize("m,n,head,tail", [(8192, 16384, 48, 400), (32768, 65536, 0, 40)])
+def test_full_size_invariants(lp, oracle, m, n, head, tail):
+    """C3 / C4 on one GPU: first pivots bit-exact against the engine-order oracle (C3 only: the oracle needs the
+    matrix on the host), then properties that hold at any size: windows replay bit for bit, the objective never
+    decreases, x_b stays feasible, B^-1 times a basic column is a unit vector, y = c_b B^-1."""
+    rng = np.random.default_rng(5)
+    with lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 30) as e:
+        e.generate_dense(1)
+        if head:
+            A, b, c = oracle.gen_dense(m, n, 1)
+            ref = oracle.solve(A, b, c, eps=1e-9, max_iter=head, order=1)
+            r = e.run(head)
+            tr = e.trace()
+            assert tr[:, 0].tolist() == ref.trace_p.tolist() and tr[:, 1].tolist() == ref.trace_q.tolist()
+            x_b, b_ixs, y = e.download()
+            assert np.array_equal(x_b, ref.x_b) and np.array_equal(b_ixs, ref.b_ixs) and r["z"] == ref.z
+            del A
+        z_prev = e.run(0)["z"]
+        for _ in range(4):
+            r = e.run(tail // 4)
+            assert r["z"] >= z_prev and r["status"] == lp.SolveStatus.MaxIter
+            z_prev = r["z"]
+        x_b, b_ixs, y = e.download()
+        trace1 = e.trace()
+        assert x_b.min() >= -1e-9 * max(1.0, np.abs(x_b).max())
+        assert len(set(b_ixs.tolist())) == m                                  # a basis: m distinct columns
+        # B^-1 . A[:, b_ixs[k]] = e_k on a sample of basis positions (rows of B^-1 come back one window at a time)
+        Binv = e.download_binv()
+        for k in rng.choice(m, 6, replace=False):
+            col = _column(m, n, int(b_ixs[k]))
+            u = Binv @ col
+            u[k] -= 1.0
+            assert np.abs(u).max() < 1e-8, (k, np.abs(u).max())
+        # y = c_b . B^-1 on a sample of columns (v4:353-356 keeps it by a linear update)
+        c = np.array([0.0] * n)
+        from simplex_method_gpu_b200.solver import lpgen_dense_into
+        bb = np.empty(m)
+        lpgen_dense_into(0, bb.ctypes.data, c.ctypes.data, m, n, 0, 0, 1)
+        cb = c[b_ixs]
+        for j in rng.choice(m, 6, replace=False):
+            assert abs(cb @ Binv[:, j] - y[j]) <= 1e-8 * max(1.0, abs(y[j]))
+        assert abs(cb @ x_b - z_prev) <= 1e-9 * max(1.0, abs(z_prev))         # z = c_b . x_b (v4:365)
+        del Binv
+        # the same windows again from the slack basis: identical pivots, identical bits
+        e.reset()
+        if head:
+            e.run(head)
+        for _ in range(4):
+            r2 = e.run(tail // 4)
+        assert r2["z"] == z_prev and np.array_equal(e.trace(), trace1)
+        x_b2, b_ixs2, _ = e.download()
+        assert np.array_equal(x_b2, x_b) and np.array_equal(b_ixs2, b_ixs)
