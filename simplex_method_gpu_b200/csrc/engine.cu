@@ -8,8 +8,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -715,16 +717,27 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 	if (!A || !b || !c) return fail(B200LP_ERR_ARG, "A, b, c must not be NULL");
 	b200lp_options o;
 	if (opt) o = *opt; else b200lp_default_options(&o);
+	using Clk = std::chrono::steady_clock;
+	auto ms_since = [](Clk::time_point t) { return std::chrono::duration<double, std::milli>(Clk::now() - t).count(); };
+	const bool timing = std::getenv("B200LP_TIMING") != nullptr;    // host wall-clock split of the call on stderr
+	auto t_all = Clk::now(), t = t_all;
+	double ms_create = 0, ms_up = 0, ms_run = 0, ms_down = 0;
 	b200lp_engine* e = nullptr;
 	int rc = create_engine<T>(m, n, &o, &e);
 	if (rc) return rc;
+	ms_create = ms_since(t);
 	b200lp_result r;
 	std::memset(&r, 0, sizeof(r));
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	do {
+		t = Clk::now();
 		if ((rc = e->upload(A, b, c))) break;
+		ms_up = ms_since(t);
+		t = Clk::now();
 		if ((rc = e->run_async(o.max_iter))) break;
 		if ((rc = e->wait(&r))) break;
+		ms_run = ms_since(t);
+		t = Clk::now();
 		cudaEventCreate(&t0);
 		cudaEventCreate(&t1);
 		cudaEventRecord(t0, e->stream);
@@ -735,11 +748,17 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 		float ms = 0;
 		cudaEventElapsedTime(&ms, t0, t1);
 		r.ms_download = ms;
+		ms_down = ms_since(t);
 	} while (0);
 	if (t0) cudaEventDestroy(t0);
 	if (t1) cudaEventDestroy(t1);
 	if (res) *res = r;
+	t = Clk::now();
 	delete e;
+	if (timing)
+		std::fprintf(stderr, "[b200lp] solve %lldx%lld: create %.1f ms, upload %.1f ms (copy %.1f), run %.1f ms (kernel %.1f), "
+			"download %.1f ms, destroy %.1f ms, total %.1f ms\n", (long long)m, (long long)n, ms_create, ms_up, r.ms_upload,
+			ms_run, r.ms_solve, ms_down, ms_since(t), ms_since(t_all));
 	return rc;
 }
 
