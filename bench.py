@@ -69,8 +69,10 @@ def time_to_optimal(name, wl, dev=0):
     r = eng.run(1 << 40)
     wall = time.perf_counter() - t0
     x_b, b_ixs, y = eng.download()
+    drift, scale = eng.check_basis()          # |B^-1 b - x_b| after all those rank-1 updates without a refactorisation
     eng.close()
     out = {"workload": f"{name}: dense LP m={m} n={n}, seed {SEED}, slack basis to optimum", "status": int(r["status"]),
+           "basis_drift": {"max_abs_Binv_b_minus_x_b": drift, "max_abs_x_b": scale},
            "pivots": int(r["pivots"]), "iterations": int(r["iterations"]), "z": r["z"],
            "seconds": r["ms_solve"] * 1e-3, "wall_seconds": wall, "pivots_per_s": r["pivots"] / (r["ms_solve"] * 1e-3)}
     out["certificate"] = optimality_certificate(m, n, x_b, b_ixs, y, r["z"])

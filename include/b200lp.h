@@ -162,6 +162,12 @@ int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols); /* st
 int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int64_t ncols,
 		const void* b, const void* c);
 
+/* ---- numerical health (the reference lists refactorisation / small-pivot guards as open, README.md:29-30) ----
+ * max_i |(B^-1 b)_i - x_b_i| and max_i |x_b_i| after flushing a pending rank-1 update: how far the product-form
+ * inverse and the linearly updated x_b (v4:347-348) have drifted apart.  One extra pass over B^-1; call it between
+ * runs (it overwrites alpha).  Changes nothing the loop reads afterwards.  Single GPU. */
+int b200lp_check_basis(b200lp_engine* e, double* xb_err, double* xb_scale);
+
 /* ---- in-kernel phase profile (options.profile > 0) ----
  * CTA 0 of the persistent kernel stamps %globaltimer (ns) at every phase boundary; one record of
  * b200lp_profile_stamps() values per iteration of the LAST launch (0 = point not reached).

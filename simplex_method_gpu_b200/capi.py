@@ -21,7 +21,7 @@ EXPORTS = [
     "b200lp_last_error", "b200lp_version",
     "b200lp_create_sharded", "b200lp_ipc_handle_bytes", "b200lp_ipc_export", "b200lp_ipc_import", "b200lp_shard_rows",
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
-    "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile",
+    "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile", "b200lp_check_basis",
     # include/b200lp_io.h
     "b200lp_read_lp", "b200lp_write_lp_text", "b200lp_write_lp_binary", "b200lp_free_problem",
 ]
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         "b200lp_shard_columns": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "b200lp_upload_columns": (C.c_int, [vp, vp, i64, i64, vp, vp]),
         "b200lp_lpgen_dense_host": (C.c_int, [i32, vp, vp, vp, i64, i64, i64, i64, C.c_uint64]),
+        "b200lp_check_basis": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "b200lp_profile_stamps": (C.c_int, []),
         "b200lp_profile_names": (C.c_char_p, []),
         "b200lp_download_profile": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +56,7 @@ struct b200lp_engine {
 	virtual int ipc_import(const void* all, int nranks) = 0;
 	virtual int shard_rows(int64_t* row0, int64_t* rows) = 0;
 	virtual int download_profile(uint64_t* out, int64_t cap_iters, int64_t* n_iters) = 0;
+	virtual int check_basis(double* xb_err, double* xb_scale) = 0;
 	cudaStream_t stream = nullptr;
 	int rank = 0, nranks = 1;
 	int grid = 0;
@@ -374,6 +376,43 @@ public:
 		const long long rows = std::max<long long>(0, std::min<long long>(d.m, d.row0 + d.ldb) - d.row0);
 		if (rows > 0)
 			CU(cudaMemcpy2D(Binv, rows * sizeof(T), d.B, d.ldb * sizeof(T), rows * sizeof(T), (size_t)d.m, cudaMemcpyDeviceToHost));
+		return B200LP_OK;
+	}
+
+	// numerical health of the product-form inverse: max_i |(B^-1 b)_i - x_b_i|.  One extra pass over B^-1, between runs.
+	int check_basis(double* xb_err, double* xb_scale) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "check_basis before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "check_basis is single-GPU only");
+		CU(cudaSetDevice(opt.device));
+		if (in_flight) { int rc = wait(nullptr); if (rc) return rc; }
+		if (hc.pending) {
+			launch_update_ftran(true, false, 0);
+			CU(cudaGetLastError());
+			hc.pending = 0;
+			CU(push_ctl());
+		}
+		CU(zero_tickets());
+		const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
+		const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
+		const int g = (int)std::max<long long>(1, std::min<long long>(tiles, grid));
+		if (wc == 1) k_ftran_vec<T, 1><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else if (wc == 2) k_ftran_vec<T, 2><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else if (wc == 4) k_ftran_vec<T, 4><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else k_ftran_vec<T, 8><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		k_ratio<T><<<grid, NT, 0, stream>>>(d);          // sums the chunk partials into alpha (the candidates are ignored)
+		launches += 2;
+		CU(cudaGetLastError());
+		std::vector<T> a((size_t)d.m), x((size_t)d.m);
+		CU(cudaMemcpyAsync(a.data(), d.alpha, d.m * sizeof(T), cudaMemcpyDeviceToHost, stream));
+		CU(cudaMemcpyAsync(x.data(), d.x_b, d.m * sizeof(T), cudaMemcpyDeviceToHost, stream));
+		CU(cudaStreamSynchronize(stream));
+		double err = 0, scale = 0;
+		for (long long i = 0; i < d.m; ++i) {
+			err = std::max(err, std::fabs((double)a[i] - (double)x[i]));
+			scale = std::max(scale, std::fabs((double)x[i]));
+		}
+		if (xb_err) *xb_err = err;
+		if (xb_scale) *xb_scale = scale;
 		return B200LP_OK;
 	}
 
@@ -842,6 +881,7 @@ int b200lp_ipc_export(b200lp_engine* e, void* out) { NEED(e); if (!out) return f
 int b200lp_ipc_import(b200lp_engine* e, const void* all, int32_t nranks) { NEED(e); if (!all) return fail(B200LP_ERR_ARG, "handles are NULL"); return e->ipc_import(all, nranks); }
 int b200lp_shard_rows(b200lp_engine* e, int64_t* row0, int64_t* rows) { NEED(e); return e->shard_rows(row0, rows); }
 int b200lp_shard_columns(b200lp_engine* e, int64_t* col0, int64_t* ncols) { NEED(e); return e->shard_columns(col0, ncols); }
+int b200lp_check_basis(b200lp_engine* e, double* xb_err, double* xb_scale) { NEED(e); return e->check_basis(xb_err, xb_scale); }
 int b200lp_profile_stamps(void) { return NSTAMP; }
 const char* b200lp_profile_names(void) { return PROFILE_NAMES_JSON; }
 int b200lp_download_profile(b200lp_engine* e, uint64_t* out, int64_t cap_iters, int64_t* n_iters) { NEED(e); return e->download_profile(out, cap_iters, n_iters); }

@@ -1240,6 +1240,14 @@ __global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p, int 
 	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, dyn, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
 }
 
+// alpha_part <- chunk partials of B^-1 v for an arbitrary device vector v (length ld): the FTRAN pass alone
+template <typename T, int WC>
+__global__ void __launch_bounds__(NT) k_ftran_vec(Dev<T> d, const T* v) {
+	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char dyn[];
+	update_ftran_phase<T, WC, false, true>(d, sh, dyn, v, 0, false, blockIdx.x, gridDim.x);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT) k_ratio(Dev<T> d) {
 	__shared__ Smem sh;

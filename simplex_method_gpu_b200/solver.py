@@ -186,6 +186,12 @@ class Engine:
         capi.check(self._L.b200lp_download_vector(self._h, which, _vp(out)))
         return out
 
+    def check_basis(self):
+        """(max |B^-1 b - x_b|, max |x_b|): drift between the product-form inverse and the linearly updated x_b."""
+        err, scale = C.c_double(0), C.c_double(0)
+        capi.check(self._L.b200lp_check_basis(self._h, C.byref(err), C.byref(scale)))
+        return err.value, scale.value
+
     def profile(self, cap: int = 1 << 16) -> np.ndarray:
         """Phase time stamps (ns) of the last persistent launch, shape (iterations, stamps); needs profile=N."""
         ns = self._L.b200lp_profile_stamps()

@@ -229,6 +229,25 @@ def test_windows_equal_one_shot_and_binv_is_inverse(lp, oracle):
         assert r2["pivots"] == one.pivots and r2["z"] == one.z
 
 
+def test_check_basis_reports_drift_and_leaves_the_run_untouched(lp, oracle):
+    m, n = 512, 1024
+    A, b, c = oracle.gen_dense(m, n, 1)
+    one = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    with lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 20) as e:
+        e.upload(A, b, c)
+        err0, scale0 = e.check_basis()
+        assert err0 == 0.0 and scale0 == np.abs(b).max()                    # slack basis: B^-1 = I, x_b = b
+        e.run(150)
+        err, scale = e.check_basis()                                         # mid-run, with a pending update
+        assert 0 <= err <= 1e-9 * scale
+        r = e.run(1 << 20)                                                   # the check must not disturb the path
+        assert r["pivots"] == one.pivots and r["z"] == one.z and np.array_equal(e.trace(), one.trace)
+        err, scale = e.check_basis()
+        x_b, b_ixs, _ = e.download()
+        want = np.abs(np.linalg.solve(A[:, b_ixs], b) - x_b).max()
+        assert err <= 1e-9 * scale and want <= 1e-9 * scale
+
+
 def test_phase_entry_points_against_numpy(lp, oracle):
     """One pivot through the per-phase C entry points, each checked on its own."""
     m, n = 200, 520
