@@ -186,6 +186,36 @@ def test_golden_traces_on_gpu(lp, oracle):
         assert abs(sol.z - g["z"]) <= 1e-9 * max(1.0, abs(g["z"])), name
 
 
+def test_small_shape_fuzz_bit_exact(lp, oracle):
+    """Ragged tiny shapes, including n == m (no structural column), optimal-at-start, unbounded and degenerate
+    LPs: status, iteration count, pivot sequence and every bit of x_b / z equal the engine-order oracle."""
+    rng = np.random.default_rng(20261018)
+    seen = set()
+    for case in range(60):
+        m = int(rng.integers(1, 41))
+        n = m + int(rng.integers(0, 61))
+        ns = n - m
+        A = np.zeros((m, n), order="F")
+        A[:, :ns] = rng.uniform(-0.3 if case % 3 == 0 else 0.0, 1.0, (m, ns))
+        A[:, ns:] = np.eye(m)
+        b = rng.uniform(1.0, 2.0, m) * max(ns, 1)
+        if case % 5 == 0:
+            b[rng.integers(0, m)] = 0.0                                   # degenerate vertex, zero-length steps
+        c = np.concatenate([rng.uniform(-0.5 if case % 4 == 0 else 0.1, 1.0, ns), np.zeros(m)])
+        if case % 7 == 0:
+            c[:ns] = -np.abs(c[:ns])                                      # optimal at the slack basis
+        for dt, eps in ((np.float64, 1e-9), (np.float32, 1e-4)):
+            Ad, bd, cd = A.astype(dt), b.astype(dt), c.astype(dt)
+            ref = oracle.solve(Ad, bd, cd, eps=eps, max_iter=500, order=1)
+            sol = lp.solve(Ad, bd, cd, eps=eps, max_iter=500)
+            tag = (case, m, n, dt.__name__)
+            assert int(sol.status) == ref.status and sol.iterations == ref.iterations and sol.pivots == ref.pivots, tag
+            assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist(), tag
+            assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs) and sol.z == ref.z, tag
+            seen.add(ref.status)
+    assert {oracle.OPTIMUM, oracle.UNBOUNDED} <= seen                     # both outcomes were exercised
+
+
 # ---------------------------------------------------------------- engine properties
 
 def test_geometry_independence(lp, oracle):
