@@ -301,6 +301,7 @@ public:
 			return B200LP_OK;
 		}
 		if (opt.mode == 1 && nranks == 1) return run_phases(iters);
+		if (tiny_ok()) return run_tiny(iters);
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
 		if (d.prof_cap > 0) CU(cudaMemsetAsync(d.prof, 0, (size_t)d.prof_cap * NSTAMP * sizeof(unsigned long long), stream));
@@ -679,6 +680,27 @@ private:
 		if (wc == 1) LAUNCH_UF(1); else if (wc == 2) LAUNCH_UF(2); else if (wc == 4) LAUNCH_UF(4); else LAUNCH_UF(8);
 #undef LAUNCH_UF
 		launches++;
+	}
+
+	// tiny LPs (one warp-wide vector row, everything fits in shared memory): the shared-memory-resident kernel.
+	// Only with the automatic grid: an explicit grid_ctas asks for the general kernel.
+	bool tiny_ok() const {
+		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0) return false;
+		if (d.ld != 32 * VecT<T>::N) return false;
+		return TinyLayout<T>(d.m, d.n, d.ns).bytes(d.m) <= (size_t)200 * 1024;
+	}
+
+	int run_tiny(int64_t iters) {
+		hc.it_end = hc.iter + iters;
+		CU(push_ctl());
+		const size_t smem = TinyLayout<T>(d.m, d.n, d.ns).bytes(d.m);
+		CU(cudaFuncSetAttribute(simplex_tiny<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CU(cudaEventRecord(ev0, stream));
+		simplex_tiny<T><<<1, NT, smem, stream>>>(d);
+		launches++;
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(ev1, stream));
+		return B200LP_OK;
 	}
 
 	// mode 1: the loop of v4:286-359 driven from the host, one launch per phase and

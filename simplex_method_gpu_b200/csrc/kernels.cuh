@@ -907,6 +907,224 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	}
 }
 
+// ---------------------------------------------------------------- tiny LPs: everything in shared memory
+//
+// Klee-Minty (m = 20, 2^20 - 1 pivots) and friends: the matrices fit in one SM's shared memory and a pivot is
+// pure latency.  One CTA, state loaded once, ~10 __syncthreads per pivot, no global round trip inside the loop
+// (the general kernel with a 1-CTA grid spends ~19 us per pivot on ~20 dependent L2 round trips).
+// Condition (host): ld == one warp-wide vector row (m <= 64 doubles / 128 floats) and A, B^-1 fit.
+// Every sum is associated exactly as in the general kernel (see the file header), so results are bit-identical:
+//   pricing dot ... the column's 32 vectors sit in warp 0's slots; the other 7 warp sums are +0
+//   FTRAN ......... 8 sub-blocks of 32 columns, one fma chain each (empty ones stay +0), the same pairwise tree
+//   O(m) dots ..... a single 256-element slice
+// State is read from and written back to the same global buffers, so windows, downloads and the phase entry
+// points see no difference.
+template <typename T>
+struct TinyLayout {
+	static constexpr int VN = VecT<T>::N;
+	static constexpr int LD = 32 * VN;
+	// element offsets into the dynamic shared memory (all multiples of LD, hence 16-byte aligned)
+	long long A, B, y, x_b, c_b, alpha, E_q, row_q, b, part, c, end;
+	int* b_ixs;
+	__host__ __device__ TinyLayout(long long m, long long n, long long ns) {
+		long long o = 0;
+		A = o; o += LD * ns;
+		B = o; o += LD * m;
+		y = o; o += LD; x_b = o; o += LD; c_b = o; o += LD; alpha = o; o += LD;
+		E_q = o; o += LD; row_q = o; o += LD; b = o; o += LD;
+		part = o; o += 8 * LD;
+		c = o; o += (n + 3) / 4 * 4;
+		end = o;
+		b_ixs = nullptr;
+	}
+	__host__ __device__ size_t bytes(long long m) const { return (size_t)end * sizeof(T) + (size_t)m * sizeof(int) + 16; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT, 1) simplex_tiny(Dev<T> d) {
+	using V = typename VecT<T>::V;
+	using M = Mem<T>;
+	constexpr int VN = VecT<T>::N;
+	constexpr int LD = 32 * VN;
+	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char dynraw[];
+	T* S = reinterpret_cast<T*>(dynraw);
+	const TinyLayout<T> L(d.m, d.n, d.ns);
+	T *sA = S + L.A, *sB = S + L.B, *sy = S + L.y, *sx = S + L.x_b, *scb = S + L.c_b, *sal = S + L.alpha,
+	  *sE = S + L.E_q, *srq = S + L.row_q, *sb = S + L.b, *spart = S + L.part, *sc = S + L.c;
+	int* sbix = reinterpret_cast<int*>(S + L.end);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int m = (int)d.m, n = (int)d.n, ns = (int)d.ns;
+	Ctl* ctl = d.ctl;
+
+	// ---- state in
+	for (long long e = tid; e < (long long)LD * ns; e += NT) sA[e] = d.A[e];
+	for (long long e = tid; e < (long long)LD * m; e += NT) sB[e] = d.B[e];
+	for (int i = tid; i < LD; i += NT) {
+		sy[i] = d.y[i]; sx[i] = d.x_b[i]; scb[i] = d.c_b[i]; sal[i] = d.alpha[i];
+		sE[i] = d.E_q[i]; srq[i] = d.row_q[i]; sb[i] = d.b[i];
+	}
+	for (int j = tid; j < n; j += NT) sc[j] = d.c[j];
+	for (int i = tid; i < m; i += NT) sbix[i] = d.b_ixs[i];
+	long long it = ctl->iter, pivots = ctl->pivots;
+	const long long it_end = ctl->it_end;
+	int pending = ctl->pending;
+	int status = 0, done = 0;
+	long long p = ctl->p, q = ctl->q;
+	double min_e = ctl->min_e;
+	__syncthreads();
+
+	while (it < it_end) {
+		// ---- pricing (v4:288-302): warp w takes columns w, w+8, ...; the column's 32 vectors are this warp's lanes
+		double best_v = CUDART_INF;
+		long long best_i = LLONG_MAX;
+		const V yv = *reinterpret_cast<const V*>(sy + lane * VN);
+		for (int col = warp; col < ns; col += NWARP) {
+			const V av = *reinterpret_cast<const V*>(sA + (long long)col * LD + lane * VN);
+			T s = fma_t(M::get(av, 0), M::get(yv, 0), T(0));
+#pragma unroll
+			for (int v = 1; v < VN; ++v) s = s + fma_t(M::get(av, v), M::get(yv, v), T(0));
+			s = warp_butterfly_sum(s);
+			s = s + T(0);                              // + the seven empty warp sums of the general kernel
+			const double e = (double)(s - sc[col]);
+			if (lane == 0 && cand_better(e, col, best_v, best_i)) { best_v = e; best_i = col; }
+		}
+		for (int k = tid; k < n - ns; k += NT) {       // unit (slack) columns
+			const double e = (double)(sy[k] - sc[ns + k]);
+			if (cand_better(e, ns + k, best_v, best_i)) { best_v = e; best_i = ns + k; }
+		}
+		block_argmin(best_v, best_i, sh);
+		min_e = best_v;
+		p = best_i;
+		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
+
+		// ---- pending rank-1 update fused with the FTRAN of column p (v4:333 + v4:307-308)
+		{
+			const int j0 = warp * SUBW;                // this warp's 32-column sub-block
+			T acc[VN];
+			V Ev = *reinterpret_cast<const V*>(sE + lane * VN);
+#pragma unroll
+			for (int v = 0; v < VN; ++v) acc[v] = T(0);
+			const int jend = j0 + SUBW < m ? j0 + SUBW : m;
+			for (int j = j0; j < jend; ++j) {
+				V x = *reinterpret_cast<const V*>(sB + (long long)j * LD + lane * VN);
+				const T a = p < ns ? sA[(long long)p * LD + j] : (j == (int)(p - ns) ? T(1) : T(0));
+				if (pending) {
+					const T r = srq[j];
+#pragma unroll
+					for (int v = 0; v < VN; ++v) M::set(x, v, fma_t(M::get(Ev, v), r, M::get(x, v)));
+					*reinterpret_cast<V*>(sB + (long long)j * LD + lane * VN) = x;
+				}
+#pragma unroll
+				for (int v = 0; v < VN; ++v) acc[v] = fma_t(M::get(x, v), a, acc[v]);
+			}
+#pragma unroll
+			for (int v = 0; v < VN; ++v) spart[(warp * 32 + lane) * VN + v] = acc[v];
+		}
+		pending = 0;
+		__syncthreads();
+		if (warp == 0) {
+			T t[NWARP][VN];
+#pragma unroll
+			for (int c = 0; c < NWARP; ++c)
+#pragma unroll
+				for (int v = 0; v < VN; ++v) t[c][v] = spart[(c * 32 + lane) * VN + v];
+#pragma unroll
+			for (int w = 1; w < NWARP; w <<= 1)
+#pragma unroll
+				for (int c = 0; c + w < NWARP; c += 2 * w)
+#pragma unroll
+					for (int v = 0; v < VN; ++v) t[c][v] = t[c][v] + t[c + w][v];
+#pragma unroll
+			for (int v = 0; v < VN; ++v) sal[lane * VN + v] = t[0][v];
+		}
+		__syncthreads();
+
+		// ---- ratio test (v4:311-325)
+		best_v = CUDART_INF;
+		best_i = LLONG_MAX;
+		long long elig = 0;
+		for (int i = tid; i < m; i += NT) {
+			const T a = sal[i];
+			if (a > T(0)) {
+				++elig;
+				const double th = (double)(sx[i] / a);
+				if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+			}
+		}
+		block_argmin(best_v, best_i, sh);
+		q = best_i;
+#pragma unroll
+		for (int off = 16; off >= 1; off >>= 1) elig += __shfl_xor_sync(0xffffffffu, elig, off);
+		__syncthreads();
+		if (lane == 0) sh.red_c[warp] = elig;
+		__syncthreads();
+		elig = 0;
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) elig += sh.red_c[w];
+		if (elig == 0) { status = 2; done = 1; ++it; break; }
+
+		// ---- pivot (v4:331-356): one 256-element slice
+		const T alpha_q = sal[q];
+		const T c_p = sc[p];
+		T t1 = T(0), t2 = T(0), eq = T(0), rq = T(0);
+		const int i = tid;
+		if (i < m) {
+			rq = sB[(long long)i * LD + q];
+			eq = (i != q) ? (-sal[i] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			T cb = scb[i];
+			if (i == q) { sh.bc_v = (double)cb; cb = c_p; }
+			t1 = fma_t(rq, sb[i], T(0));
+			t2 = fma_t(cb, eq, T(0));
+		}
+		t1 = warp_butterfly_sum(t1);
+		t2 = warp_butterfly_sum(t2);
+		__syncthreads();
+		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; }
+		if (i < LD) { srq[i] = i < m ? rq : T(0); sE[i] = i < m ? eq : T(0); }
+		__syncthreads();
+		T sxv = T(0), syv = T(0);
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) { sxv = sxv + (T)sh.dsum[0][w]; syv = syv + (T)sh.dsum[1][w]; }
+		sxv = T(0) + sxv;                              // book2 of the general kernel starts its slice sum from 0
+		syv = T(0) + syv;
+		syv += c_p - (T)sh.bc_v;
+		if (i < m) {
+			sx[i] = fma_t(sxv, eq, sx[i]);
+			sy[i] = fma_t(syv, rq, sy[i]);
+			if (i == q) { scb[i] = c_p; sbix[i] = (int)p; }
+		}
+		if (tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
+		pending = 1;
+		++pivots;
+		++it;
+		__syncthreads();
+	}
+
+	// ---- state out
+	__syncthreads();
+	for (long long e = tid; e < (long long)LD * m; e += NT) d.B[e] = sB[e];
+	for (int k = tid; k < LD; k += NT) {
+		d.y[k] = sy[k]; d.x_b[k] = sx[k]; d.c_b[k] = scb[k]; d.alpha[k] = sal[k]; d.E_q[k] = sE[k]; d.row_q[k] = srq[k];
+	}
+	for (int k = tid; k < m; k += NT) d.b_ixs[k] = sbix[k];
+	// z = c_b . x_b in slice order (v4:365)
+	T t = tid < m ? fma_t(scb[tid], sx[tid], T(0)) : T(0);
+	t = warp_butterfly_sum(t);
+	__syncthreads();
+	if (lane == 0) sh.dsum[0][warp] = (double)t;
+	__syncthreads();
+	if (tid == 0) {
+		T a = T(0);
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[0][w];
+		const T z = T(0) + a;
+		ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
+		ctl->status = status; ctl->done = done;
+		ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = (double)z; ctl->c_b_q = sh.bc_v;
+	}
+}
+
 // ---------------------------------------------------------------- sharded (multi-GPU) loop
 //
 // One process per GPU, the same persistent kernel on every rank.  B^-1 is row-block

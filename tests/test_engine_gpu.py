@@ -146,6 +146,30 @@ def test_klee_minty_exact(lp, oracle, d):
     assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs)
 
 
+def test_tiny_kernel_windows_and_state_round_trip(lp, oracle):
+    """The shared-memory kernel reads and writes the same global state as the general one: uneven windows,
+    B^-1 download, reset and the general kernel (explicit grid) all agree bit for bit."""
+    A, b, c = oracle.gen_klee_minty(9)
+    one = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20, grid_ctas=1)          # general kernel
+    assert one.pivots == 2 ** 9 - 1
+    m, n = A.shape
+    with lp.Engine(m, n, np.float64, eps=1e-4, max_iter=1 << 20) as e:         # auto -> shared-memory kernel
+        e.upload(A, b, c)
+        while True:
+            r = e.run(37)
+            if r["status"] != lp.SolveStatus.MaxIter:
+                break
+        assert r["pivots"] == one.pivots and r["z"] == one.z and r["iterations"] == one.iterations
+        x_b, b_ixs, y = e.download()
+        assert np.array_equal(x_b, one.x_b) and np.array_equal(b_ixs, one.b_ixs) and np.array_equal(e.trace(), one.trace)
+        Binv = e.download_binv()
+        assert np.abs(A[:, b_ixs] @ Binv - np.eye(m)).max() < 1e-9
+        err, scale = e.check_basis()
+        assert err <= 1e-12 * scale
+        e.reset()
+        assert e.run(1 << 20)["z"] == one.z
+
+
 def test_klee_minty_20_full_config(lp, oracle):
     """BASELINE config 5a at full size: 2^20 - 1 pivots, optimum 5^20, every pivot identical to the oracle's."""
     A, b, c = oracle.gen_klee_minty(20)
@@ -207,11 +231,13 @@ def test_small_shape_fuzz_bit_exact(lp, oracle):
         for dt, eps in ((np.float64, 1e-9), (np.float32, 1e-4)):
             Ad, bd, cd = A.astype(dt), b.astype(dt), c.astype(dt)
             ref = oracle.solve(Ad, bd, cd, eps=eps, max_iter=500, order=1)
-            sol = lp.solve(Ad, bd, cd, eps=eps, max_iter=500)
-            tag = (case, m, n, dt.__name__)
-            assert int(sol.status) == ref.status and sol.iterations == ref.iterations and sol.pivots == ref.pivots, tag
-            assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist(), tag
-            assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs) and sol.z == ref.z, tag
+            # auto = the shared-memory kernel for these sizes; an explicit grid = the general kernel (1 CTA, 3 CTAs)
+            for kw in (dict(), dict(grid_ctas=1), dict(grid_ctas=3)):
+                sol = lp.solve(Ad, bd, cd, eps=eps, max_iter=500, **kw)
+                tag = (case, m, n, dt.__name__, kw)
+                assert int(sol.status) == ref.status and sol.iterations == ref.iterations and sol.pivots == ref.pivots, tag
+                assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist(), tag
+                assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs) and sol.z == ref.z, tag
             seen.add(ref.status)
     assert {oracle.OPTIMUM, oracle.UNBOUNDED} <= seen                     # both outcomes were exercised
 
