@@ -84,6 +84,22 @@ def test_oracle_and_engine_match_reference_f64(oracle, engine_lib, m, n, seed):
         assert abs(z - ref.z) <= 1e-9 * abs(ref.z), name
 
 
+@pytest.mark.parametrize("m,n,seed", [(64, 160, 2), (200, 456, 3)])
+def test_engine_matches_reference_f32(oracle, engine_lib, m, n, seed):
+    """The reference's stock scalar type (`using real = float`, v4:12).  fp32 sums differ in the last bits between
+    cuBLAS and the engine, so near-ties may swap pivots; the optimum must agree to fp32 accuracy and the first
+    pivots (large gaps) must be the same."""
+    _need_ref(oracle, np.float32)
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(m, n, seed, dtype=np.float32)
+    ref = oracle.ref_solve(A, b, c, eps=1e-4, max_iter=100000)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=100000)
+    assert ref.status == oracle.OPTIMUM and sol.status == lp.SolveStatus.OptimumFound
+    assert abs(sol.z - ref.z) <= 5e-4 * abs(ref.z)
+    k = min(8, len(ref.trace_p), len(sol.trace))
+    assert sol.trace[:k, 0].tolist() == ref.trace_p[:k].tolist() and sol.trace[:k, 1].tolist() == ref.trace_q[:k].tolist()
+
+
 def test_reference_exact_problems(oracle, engine_lib):
     _need_ref(oracle)
     import simplex_method_gpu_b200 as lp
