@@ -104,7 +104,6 @@ public:
 		CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 		CU(cudaEventCreate(&ev0));
 		CU(cudaEventCreate(&ev1));
-		CU(cudaEventCreate(&ev2));
 
 		const size_t ld = (size_t)d.ld, m = (size_t)d.m;
 		CU(alloc(&d.B, (size_t)d.ldb * m));
@@ -609,7 +608,6 @@ private:
 		if (pinned) cudaFreeHost(pinned);
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
-		if (ev2) cudaEventDestroy(ev2);
 		if (stream) cudaStreamDestroy(stream);
 	}
 
@@ -637,7 +635,7 @@ private:
 		*st = hc;
 		st->bar = 0;
 		st->price_ctr = st->upd_ctr = 0;
-		st->xarr[0] = st->xarr[1] = st->xarr[2] = 0;
+		st->xarr[0] = st->xarr[1] = 0;
 		cudaError_t e = cudaMemcpyAsync(d.ctl, st, sizeof(Ctl), cudaMemcpyHostToDevice, stream);
 		if (e != cudaSuccess) return e;
 		// the staging buffer is reused: make sure the copy has been consumed
@@ -742,7 +740,7 @@ private:
 	void* pinned = nullptr;
 	std::vector<void*> owned, opened;
 	bool peers_mapped = false;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	int num_sms = 0, max_grid = 0, wc = 1;
 	bool have_data = false, in_flight = false;
 	int64_t launches = 0;

@@ -76,7 +76,7 @@ struct Ctl {
 	int pending;              // rank-1 update (E_q, row_q) not yet applied to B^-1
 	int done;                 // optimum / unbounded reached
 	int bad;                  // a wait timed out (sharded mode)
-	unsigned long long xarr[3];       // arrivals at the three exchanges (reset by the host before a launch)
+	unsigned long long xarr[2];       // arrivals at the exchanges X1 / X2 (reset by the host before a launch)
 	unsigned int price_ctr;   // dynamic work tickets of the pricing phase (column groups)
 	unsigned int upd_ctr;     // dynamic work tickets of the update+FTRAN phase (tiles)
 	unsigned long long xepoch; // cross-GPU barrier epoch, monotonic over the engine's life
@@ -212,7 +212,6 @@ struct Smem {
 	double wsum[2][PRICE_NC][NWARP];  // pricing: warp sums, double buffered
 	double dsum[2][NWARP];            // O(m) dots
 	double bc_v;                      // broadcasts
-	long long bc_i;
 	long long bc_c;
 	double bc_s[2];
 	long long tk;                     // update_ftran: next dynamic tile
@@ -223,7 +222,6 @@ struct Smem {
 	unsigned long long full[PRICE_MAX_STAGES];
 	unsigned long long empty[PRICE_MAX_STAGES];
 	long long ring_group[PRICE_MAX_STAGES];   // column group held by the stage, -1 = end of stream
-	int ring_rb[PRICE_MAX_STAGES];            // row block of that group
 };
 
 // ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX)
@@ -341,18 +339,20 @@ __device__ __forceinline__ void stamp(const Dev<T>& d, long long itl, int k) {
 
 // ---------------------------------------------------------------- grid barrier
 
-// All CTAs are co-resident (cooperative launch).  One arrival per CTA on a
-// monotonically increasing counter; release/acquire through __threadfence,
-// which also invalidates L1 so plain loads after the barrier see fresh data.
+// All CTAs are co-resident (cooperative launch).  One arrival per CTA on a monotonically increasing counter:
+// a release reduction (fire and forget: nobody waits for the old value) and an acquire-load spin, so the
+// arrival costs one fence and the wake-up one L2 round trip.  The acquire also invalidates L1, so plain loads
+// after the barrier see fresh data.
 __device__ __forceinline__ void grid_barrier(Ctl* ctl, unsigned long long& epoch) {
 	epoch += gridDim.x;
 	if (gridDim.x == 1) { __syncthreads(); return; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		__threadfence();
-		atomicAdd(&ctl->bar, 1ULL);
-		while (*((volatile unsigned long long*)&ctl->bar) < epoch) { }
-		__threadfence();
+		asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(&ctl->bar) : "memory");
+		unsigned long long v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&ctl->bar) : "memory");
+		} while (v < epoch);
 	}
 	__syncthreads();
 }
@@ -436,7 +436,6 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 			unsigned char* dst = ringbuf + prod.stage * stage_bytes;
 			if (lane == 0) {
 				sh.ring_group[prod.stage] = pg;
-				sh.ring_rb[prod.stage] = prb;
 				// the phase cannot complete before this arrival, whatever the order of the copies' complete_tx
 				mbar_arrive_expect_tx(&sh.full[prod.stage], (unsigned)(nc + 1) * colbytes);
 			} else if (lane == 1) {
