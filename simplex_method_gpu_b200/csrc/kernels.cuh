@@ -1149,6 +1149,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
 	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1171,12 +1176,12 @@ __device__ __forceinline__ bool grid_barrier_t(Ctl* ctl, unsigned long long& epo
 	if (threadIdx.x == 0) {
 		bool ok = true;
 		if (gridDim.x > 1) {
-			__threadfence();
-			atomicAdd(&ctl->bar, 1ULL);
-			const unsigned long long t0 = globaltimer_ns();
-			while (*((volatile unsigned long long*)&ctl->bar) < epoch)
-				if (globaltimer_ns() - t0 > XWAIT_NS) { ok = false; break; }
-			__threadfence();
+			asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(&ctl->bar) : "memory");
+			if (ld_acquire_gpu(&ctl->bar) < epoch) {
+				const unsigned long long t0 = globaltimer_ns();
+				while (ld_acquire_gpu(&ctl->bar) < epoch)
+					if (globaltimer_ns() - t0 > XWAIT_NS) { ok = false; break; }
+			}
 		}
 		sh.bc_c = ok;
 	}
