@@ -24,6 +24,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = [("dense", 300, 700, 2, 1e-9), ("dense", 1024, 2048, 1, 1e-9), ("dense", 96, 1000, 4, 1e-9),
              ("km", 10, 20, 0, 1e-4), ("assign", 16, 0, 1, 1e-4), ("dense32", 200, 520, 3, 1e-4)]
+    if os.environ.get("SHARDED_STRESS"):       # exchange-dominated sizes, several seeds: a race would show up here first
+        cases = [("dense", 2048, 4096, s, 1e-9) for s in (1, 2, 3)] + [("dense", 640, 1400, s, 1e-9) for s in (4, 5, 6, 7)] \
+            + [("dense32", 1024, 2304, 8, 1e-4)]
     for kind, m, n, seed, eps in cases:
         dt = np.float64
         if kind == "dense":
