@@ -30,7 +30,8 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("eps", C.c_double), ("max_iter", C.c_int64), ("device", C.c_int32), ("grid_ctas", C.c_int32),
                 ("tile_shape", C.c_int32), ("check_slack", C.c_int32), ("mode", C.c_int32), ("profile", C.c_int32),
-                ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32)]
+                ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32),
+                ("price_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Result(C.Structure):

@@ -112,7 +112,8 @@ struct Dev {
 	long long row0, ldb;
 	long long col0, nsl;
 	long long k0, k1;                 // share of the unit (slack) columns priced on this rank
-	int price_nc;                     // pricing group width: 4, or 2 when a CTA would get only a few groups
+	int price_nc;                     // pricing group width of the TMA ring: 4 (or 2, option)
+	int price_direct;                 // 1: register-staged pricing without the ring (the A shard is L2 resident)
 	long long colstart[MAXR + 1], rowstart[MAXR + 1];
 	unsigned long long* prof;         // optional phase stamps (globaltimer ns), NSTAMP per iteration of a launch
 	long long prof_cap;               // iterations the buffer holds (0 = profiling off)
@@ -525,6 +526,83 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	if (tid == 0) { d.cand[part].val = best_v; d.cand[part].idx = best_i; }
 }
 
+// Pricing without the ring, for LPs whose A shard is L2 resident (m <= ~2048): there is nothing to stream from
+// HBM, a pass is a few microseconds, and the ring's start-up (barrier init, first TMA round trip, ticket atomics)
+// would be a third of it.  Register-staged 16-byte loads, 16 in flight per thread; the per-column summation order is
+// the one of price_phase (thread t owns vectors t, t+256, ...), so both give the same bits.
+template <typename T>
+__device__ void price_phase_direct(const Dev<T>& d, Smem& sh, int part, int nparts) {
+	using M = Mem<T>;
+	using V = typename VecT<T>::V;
+	constexpr int VN = VecT<T>::N;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const long long ld = d.ld;
+
+	double best_v = CUDART_INF;
+	long long best_i = LLONG_MAX;
+
+	// groups of PRICE_NC columns handed out by the ticket counter (first group = CTA index), like the tiles of
+	// the update pass: fast and slow SMs even out, results do not depend on who prices a column
+	const long long c1 = d.nsl;
+	const long long ngroups = (c1 + PRICE_NC - 1) / PRICE_NC;
+	int buf = 0;
+	for (long long g = part; g < ngroups; buf ^= 1) {
+		const long long col = g * PRICE_NC;
+		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // read after the barrier below
+		const T* ap[PRICE_NC];
+#pragma unroll
+		for (int k = 0; k < PRICE_NC; ++k) {
+			const long long cc = col + k < c1 ? col + k : c1 - 1;   // ragged tail: re-read the last column
+			ap[k] = d.A + cc * ld;
+		}
+		T acc[PRICE_NC][VN];
+#pragma unroll
+		for (int k = 0; k < PRICE_NC; ++k)
+#pragma unroll
+			for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
+
+#pragma unroll 4
+		for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
+			const V yv = *reinterpret_cast<const V*>(d.y + i);
+			V av[PRICE_NC];
+#pragma unroll
+			for (int k = 0; k < PRICE_NC; ++k) av[k] = M::ld_nc(ap[k] + i);
+#pragma unroll
+			for (int k = 0; k < PRICE_NC; ++k)
+#pragma unroll
+				for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][v]);
+		}
+#pragma unroll
+		for (int k = 0; k < PRICE_NC; ++k) {
+			T s = acc[k][0];
+#pragma unroll
+			for (int v = 1; v < VN; ++v) s = s + acc[k][v];
+			s = warp_butterfly_sum(s);
+			if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
+		}
+		__syncthreads();
+		g = sh.tk;
+		if (tid < PRICE_NC && col + tid < c1) {
+			T s = (T)sh.wsum[buf][tid][0];
+#pragma unroll
+			for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
+			const long long j = d.col0 + col + tid;     // global column index
+			const double e = (double)(s - d.c[j]);
+			if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
+		}
+		__syncthreads();                              // sh.tk is rewritten at the top of the next group
+	}
+
+	for (long long k = d.k0 + (long long)part * NT + tid; k < d.k1; k += (long long)nparts * NT) {   // unit (slack) columns
+		const double e = (double)(d.y[k] - d.c[d.ns + k]);
+		const long long j = d.ns + k;
+		if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
+	}
+
+	block_argmin(best_v, best_i, sh);
+	if (tid == 0) { d.cand[part].val = best_v; d.cand[part].idx = best_i; }
+}
+
 // ---------------------------------------------------------------- phase: update + FTRAN
 
 // One pass over B^-1:  (UPDATE) B^-1 += E_q (x) row_q   [cublasSger, v4:333]
@@ -854,7 +932,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	while (it < it_end) {
 		// ---- pricing + entering column (v4:288-302)
 		stamp(d, it - it0, 0);
-		price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		if (d.price_direct) price_phase_direct<T>(d, sh, me, G);
+		else                price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
 		stamp(d, it - it0, 1);
 		grid_barrier(ctl, epoch);
 		if (me == 0 && threadIdx.x == 0) ctl->price_ctr = 0;     // every CTA is past pricing; next use is barriers away
@@ -1364,7 +1443,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 		stamp(d, it - it0, 0);
 		++xe;
 		const int par = (int)(xe & 1);
-		price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		if (d.price_direct) price_phase_direct<T>(d, sh, me, G);
+		else                price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
 		stamp(d, it - it0, 1);
 		if (arrive_last(&ctl->xarr[0], n1 += G, sh)) publish(d, sh, 0, par, xe, false);
 		long long dummy;
@@ -1438,7 +1518,8 @@ __global__ void __launch_bounds__(NT) k_price(Dev<T> d) {
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
 	ring_init(sh, rcons, rprod, d.price_nc);
-	price_phase<T>(d, sh, ringbuf, rcons, rprod, blockIdx.x, gridDim.x);
+	if (d.price_direct) price_phase_direct<T>(d, sh, blockIdx.x, gridDim.x);
+	else                price_phase<T>(d, sh, ringbuf, rcons, rprod, blockIdx.x, gridDim.x);
 }
 
 // final argmin over the per-CTA candidates -> ctl->p / ctl->min_e (kind 0) or ctl->q + eligible (kind 1)

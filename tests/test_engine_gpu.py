@@ -250,7 +250,9 @@ def test_geometry_independence(lp, oracle):
     A, b, c = oracle.gen_dense(m, n, 9)
     base = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
     for kw in (dict(grid_ctas=1), dict(grid_ctas=7), dict(grid_ctas=148, tile_shape=1), dict(tile_shape=2),
-               dict(tile_shape=4), dict(tile_shape=8), dict(mode=1), dict(check_slack=0)):
+               dict(tile_shape=4), dict(tile_shape=8), dict(mode=1), dict(check_slack=0), dict(price_cols=2),
+               dict(price_mode=1), dict(price_mode=2), dict(price_mode=1, grid_ctas=5), dict(price_mode=2, grid_ctas=5),
+               dict(price_mode=1, mode=1), dict(price_mode=2, mode=1)):
         sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20, **kw)
         assert np.array_equal(sol.trace, base.trace), kw
         assert np.array_equal(sol.x_b, base.x_b) and sol.z == base.z and np.array_equal(sol.b_ixs, base.b_ixs), kw

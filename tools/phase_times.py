@@ -26,6 +26,7 @@ ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--shape", type=int, default=0, help="update+FTRAN tile shape (warps along columns), 0 = auto")
 ap.add_argument("--price-cols", type=int, default=0)
 ap.add_argument("--l2", type=int, default=-1, help="l2_persist_mb: -1 off, 0 max, else MiB")
+ap.add_argument("--price-mode", type=int, default=0, help="0 auto, 1 TMA ring, 2 register-staged")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 a.m, a.n = (int(x) for x in a.lp.lower().split("x"))
@@ -42,13 +43,13 @@ if world > 1:
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     e = ShardedEngine(a.m, a.n, np.float64, rank=rank, world=world, device=local, eps=1e-9, max_iter=1 << 30,
-                      profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2)
+                      profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode)
     e.generate_dense(1)
     e.connect()
     dist.barrier()
     names = names["sharded"]
 else:
-    e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2)
+    e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode)
     e.generate_dense(1)
     names = names["single"]
 
