@@ -167,3 +167,34 @@ def test_native_reader_errors_use_the_reference_messages(engine_lib, tmp_path):
     p.write_text("2 4\n1 1 1 0\n1 2 0 1\n3 4\n1 1 0\n")
     with pytest.raises(ValueError, match=r"Failed to read \(0,3\) for c"):
         read_lp_native(str(p))
+
+
+def test_native_io_round_trip_fuzz(engine_lib, tmp_path):
+    """Random shapes and awkward values (denormals, huge exponents, negative zero, integers) through text and binary."""
+    from simplex_method_gpu_b200.solver import read_lp_native, write_lp_native
+    import simplex_method_gpu_b200 as s
+    rng = np.random.default_rng(7)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, 5e-324, -2.2250738585072014e-308, 1.7976931348623157e308, 123456789.0,
+                         1e-7, 0.1, 1 / 3])
+    for case in range(25):
+        m = int(rng.integers(1, 30))
+        n = m + int(rng.integers(0, 40))
+        for dt in (np.float64, np.float32):
+            A = rng.standard_normal((m, n)) * 10.0 ** rng.integers(-12, 12, (m, n))
+            pick = rng.random((m, n)) < 0.2
+            A[pick] = rng.choice(specials, int(pick.sum()))
+            with np.errstate(over="ignore", under="ignore"):
+                A = np.asfortranarray(A.astype(dt))
+                b = (rng.standard_normal(m) * 1e3).astype(dt)
+                c = rng.choice(specials, n).astype(dt)
+            A[~np.isfinite(A)] = 1.0
+            c[~np.isfinite(c)] = 1.0
+            for binary in (False, True):
+                path = str(tmp_path / f"f{case}_{dt.__name__}_{int(binary)}")
+                write_lp_native(path, A, b, c, binary=binary)
+                A1, b1, c1 = read_lp_native(path, dtype=dt)
+                assert A1.tobytes() == A.tobytes() and b1.tobytes() == b.tobytes() and c1.tobytes() == c.tobytes(), \
+                    (case, dt.__name__, binary)                                  # bit-exact, sign of zero included
+                if not binary:
+                    A2, b2, c2 = s.read_lp(path, dtype=dt)                        # the pure-Python reader agrees
+                    assert np.array_equal(A2, A) and np.array_equal(b2, b) and np.array_equal(c2, c)
