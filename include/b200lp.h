@@ -65,7 +65,7 @@ typedef struct {
 	int32_t price_cols;   /* pricing group width: 0 = auto, else 2 | 4 columns per TMA block */
 	int32_t l2_persist_mb; /* pin the head of B^-1 in the persisting part of L2: -1 = off (default), 0 = as much as
 	                          the device allows, else MiB */
-	int32_t price_mode;   /* 0 = auto (TMA ring unless the A shard is L2 resident), 1 = TMA ring, 2 = register-staged */
+	int32_t price_mode;   /* 0 = auto (register-staged loads up to a 2 GB A shard, TMA ring above), 1 = TMA ring, 2 = register-staged */
 	int32_t reserved;
 } b200lp_options;
 

@@ -582,9 +582,11 @@ private:
 		// (measured on B200: 2-column blocks run at ~60 % of the streaming rate of 4-column blocks, which costs
 		// more than their shorter tail saves, so auto is always 4)
 		d.price_nc = (opt.price_cols == 2 || opt.price_cols == 4) ? opt.price_cols : 4;
-		// L2-resident A shard: price without the ring (a pass is a few microseconds, the ring's start-up a third of it)
+		// Pricing path (measured): register-staged loads win clearly while the A shard is L2 resident
+		// (the ring's start-up is a third of such a pass), by ~6 % of the pass at m = 8192 (512 MB) and tie with the
+		// TMA ring at 1 GB (8-GPU shard of m = 32768) and 8 GB; the ring is kept for the largest shards.
 		d.price_direct = opt.price_mode == 1 ? 0 : opt.price_mode == 2 ? 1
-		               : ((size_t)d.ld * (size_t)nsl_new * sizeof(T) <= ((size_t)48 << 20) ? 1 : 0);
+		               : ((size_t)d.ld * (size_t)nsl_new * sizeof(T) <= ((size_t)2 << 30) ? 1 : 0);
 		// unit (slack) columns priced without matrix bytes: none when the slack block was not recognised
 		const long long nunit = d.n - ns_new;
 		d.k0 = nunit * rank / nranks;

@@ -526,9 +526,10 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 	if (tid == 0) { d.cand[part].val = best_v; d.cand[part].idx = best_i; }
 }
 
-// Pricing without the ring, for LPs whose A shard is L2 resident (m <= ~2048): there is nothing to stream from
-// HBM, a pass is a few microseconds, and the ring's start-up (barrier init, first TMA round trip, ticket atomics)
-// would be a third of it.  Register-staged 16-byte loads, 16 in flight per thread; the per-column summation order is
+// Pricing without the ring.  For LPs whose A shard is L2 resident (m <= ~2048) there is nothing to stream from
+// HBM, a pass is a few microseconds and the ring's start-up (first TMA round trip, barrier handshakes) would be a
+// third of it; measured, this path also wins by ~6 % of the pass at m = 8192 and ties with the ring above that, so
+// the host selects it up to a 2 GB A shard (Engine::set_columns).  Register-staged 16-byte loads, 16 in flight per thread; the per-column summation order is
 // the one of price_phase (thread t owns vectors t, t+256, ...), so both give the same bits.
 template <typename T>
 __device__ void price_phase_direct(const Dev<T>& d, Smem& sh, int part, int nparts) {
