@@ -99,6 +99,12 @@ int b200lp_solve_f32(const float* A, const float* b, const float* c, int64_t m, 
 		const b200lp_options* opt, float* x_b, int32_t* b_ixs,
 		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
 
+/* Keep the device buffers of the last b200lp_solve_* call for the next call of the same shape, dtype and options
+ * (on != 0), or release them and go back to the reference's behaviour of leaving nothing behind (on == 0, the
+ * default).  Creating and freeing 16 GB of device memory costs 40-500 ms per call at m = 32768.  Returns the
+ * previous setting.  Thread safe; one engine is kept per process. */
+int b200lp_set_memory_cache(int32_t on);
+
 /* ---- handle API: device state survives between calls (bench, windows, tests) ---- */
 
 /* allocates A_N, B^-1 and all vectors for an m x n problem (v4:245-264) */

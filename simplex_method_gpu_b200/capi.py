@@ -14,6 +14,7 @@ F32, F64 = 0, 1
 
 EXPORTS = [
     "b200lp_default_options", "b200lp_solve_f64", "b200lp_solve_f32", "b200lp_create", "b200lp_destroy",
+    "b200lp_set_memory_cache",
     "b200lp_upload", "b200lp_generate_dense", "b200lp_reset", "b200lp_run", "b200lp_run_async", "b200lp_wait",
     "b200lp_download", "b200lp_download_binv", "b200lp_download_trace", "b200lp_phase_price",
     "b200lp_phase_update_ftran", "b200lp_phase_ratio", "b200lp_phase_pivot_update", "b200lp_download_vector",
@@ -69,6 +70,7 @@ def lib() -> C.CDLL:
         "b200lp_default_options": (None, [PO]),
         "b200lp_solve_f64": (C.c_int, [vp, vp, vp, i64, i64, PO, vp, vp, vp, i64, PR]),
         "b200lp_solve_f32": (C.c_int, [vp, vp, vp, i64, i64, PO, vp, vp, vp, i64, PR]),
+        "b200lp_set_memory_cache": (C.c_int, [i32]),
         "b200lp_create": (C.c_int, [i32, i64, i64, PO, C.POINTER(vp)]),
         "b200lp_destroy": (C.c_int, [vp]),
         "b200lp_upload": (C.c_int, [vp, vp, vp, vp]),

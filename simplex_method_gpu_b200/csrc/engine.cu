@@ -14,8 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 using namespace b200lp;
@@ -37,6 +39,8 @@ static int fail(int code, const std::string& msg) {
 struct b200lp_engine {
 	virtual ~b200lp_engine() {}
 	virtual int upload(const void* A, const void* b, const void* c) = 0;
+	virtual int upload_unchecked(const void* A, const void* b, const void* c) = 0;
+	virtual bool slack_is_identity(const void* A) const = 0;
 	virtual int upload_columns(const void* Acols, int64_t col0, int64_t ncols, const void* b, const void* c) = 0;
 	virtual int shard_columns(int64_t* col0, int64_t* ncols) = 0;
 	virtual int generate_dense(uint64_t seed) = 0;
@@ -211,6 +215,19 @@ public:
 		}
 		CU(set_columns(opt.check_slack ? n : n - m));
 		return upload_block(A + (size_t)d.col0 * m, bv, cv);
+	}
+
+	// the structural columns only, trusting the identity slack block for now (solve_once checks it while the
+	// GPU is already pivoting and starts over in the rare case that the block is data)
+	int upload_unchecked(const void* Av, const void* bv, const void* cv) override {
+		const T* A = static_cast<const T*>(Av);
+		CU(cudaSetDevice(opt.device));
+		CU(set_columns(d.n - d.m));
+		return upload_block(A + (size_t)d.col0 * d.m, bv, cv);
+	}
+
+	bool slack_is_identity(const void* Av) const override {
+		return host_is_identity(static_cast<const T*>(Av) + (size_t)(d.n - d.m) * d.m, d.m);
 	}
 
 	// sharded front door: the caller hands over only this rank's structural columns
@@ -616,16 +633,24 @@ private:
 		if (stream) cudaStreamDestroy(stream);
 	}
 
+	// Is S (m x m, column-major, host) the identity?  A streaming OR over the raw bits of every column (sign bit
+	// shifted out so that -0.0 passes like in a == comparison) with the diagonal entry checked apart: the loop
+	// vectorises and runs at memory speed, which matters because it reads m*m elements (8.6 GB at m = 32768)
+	// while the upload is on the wire.
 	static bool host_is_identity(const T* S, long long m) {
-		const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		using U = typename std::conditional<sizeof(T) == 8, uint64_t, uint32_t>::type;
+		const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
 		const unsigned nt = (unsigned)std::max<long long>(1, std::min<long long>(hw, m / 64));
 		std::atomic<bool> ok{true};
 		auto work = [&](long long j0, long long j1) {
 			for (long long j = j0; j < j1 && ok.load(std::memory_order_relaxed); ++j) {
 				const T* col = S + (size_t)j * m;
-				bool good = true;
-				for (long long i = 0; i < m; ++i) good &= (col[i] == (i == j ? T(1) : T(0)));
-				if (!good) ok.store(false, std::memory_order_relaxed);
+				if (col[j] != T(1)) { ok.store(false, std::memory_order_relaxed); return; }
+				const U* bits = reinterpret_cast<const U*>(col);
+				U acc = 0;
+				for (long long i = 0; i < j; ++i) acc |= bits[i];
+				for (long long i = j + 1; i < m; ++i) acc |= bits[i];
+				if ((U)(acc << 1) != 0) { ok.store(false, std::memory_order_relaxed); return; }
 			}
 		};
 		if (nt == 1) { work(0, m); return ok; }
@@ -775,30 +800,66 @@ int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine
 	return B200LP_OK;
 }
 
+// One engine kept between calls of b200lp_solve_* (b200lp_set_memory_cache): creating and destroying 16 GB of
+// device buffers costs 40-500 ms per call (cudaFree alone was measured at 31-449 ms), the solve of a 192-pivot
+// window 740 ms.  Off by default: like the reference, a call then leaves no device memory behind.
+struct EngineCache {
+	std::mutex mu;
+	bool on = false;
+	b200lp_engine* e = nullptr;
+	int dtype = -1;
+	int64_t m = 0, n = 0;
+	b200lp_options opt;
+};
+static EngineCache g_cache;
+
 template <typename T>
 int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b200lp_options* opt,
 		T* x_b, int32_t* b_ixs, int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
 	if (!A || !b || !c) return fail(B200LP_ERR_ARG, "A, b, c must not be NULL");
 	b200lp_options o;
 	if (opt) o = *opt; else b200lp_default_options(&o);
+	const int dtype = sizeof(T) == 8 ? B200LP_F64 : B200LP_F32;
 	using Clk = std::chrono::steady_clock;
 	auto ms_since = [](Clk::time_point t) { return std::chrono::duration<double, std::milli>(Clk::now() - t).count(); };
 	const bool timing = std::getenv("B200LP_TIMING") != nullptr;    // host wall-clock split of the call on stderr
 	auto t_all = Clk::now(), t = t_all;
 	double ms_create = 0, ms_up = 0, ms_run = 0, ms_down = 0;
 	b200lp_engine* e = nullptr;
-	int rc = create_engine<T>(m, n, &o, &e);
-	if (rc) return rc;
+	{
+		std::lock_guard<std::mutex> lk(g_cache.mu);
+		if (g_cache.on && g_cache.e && g_cache.dtype == dtype && g_cache.m == m && g_cache.n == n &&
+				std::memcmp(&g_cache.opt, &o, sizeof(o)) == 0) {
+			e = g_cache.e;                 // take it out of the cache for the duration of the call
+			g_cache.e = nullptr;
+		}
+	}
+	int rc = B200LP_OK;
+	if (!e && (rc = create_engine<T>(m, n, &o, &e))) return rc;
 	ms_create = ms_since(t);
 	b200lp_result r;
 	std::memset(&r, 0, sizeof(r));
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	do {
 		t = Clk::now();
-		if ((rc = e->upload(A, b, c))) break;
-		ms_up = ms_since(t);
-		t = Clk::now();
-		if ((rc = e->run_async(o.max_iter))) break;
+		if (o.check_slack && n > m) {
+			// optimistic: ship the structural columns and start pivoting; the m x m slack block (8.6 GB of host
+			// memory at m = 32768) is verified by host threads while the GPU works
+			if ((rc = e->upload_unchecked(A, b, c))) break;
+			ms_up = ms_since(t);
+			t = Clk::now();
+			if ((rc = e->run_async(o.max_iter))) break;
+			if (!e->slack_is_identity(A)) {           // rare: the block is data -> store and price all n columns
+				if ((rc = e->wait(nullptr))) break;
+				if ((rc = e->upload(A, b, c))) break;
+				if ((rc = e->run_async(o.max_iter))) break;
+			}
+		} else {
+			if ((rc = e->upload(A, b, c))) break;
+			ms_up = ms_since(t);
+			t = Clk::now();
+			if ((rc = e->run_async(o.max_iter))) break;
+		}
 		if ((rc = e->wait(&r))) break;
 		ms_run = ms_since(t);
 		t = Clk::now();
@@ -818,6 +879,17 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 	if (t1) cudaEventDestroy(t1);
 	if (res) *res = r;
 	t = Clk::now();
+	{
+		std::lock_guard<std::mutex> lk(g_cache.mu);
+		if (g_cache.on && rc == B200LP_OK && !g_cache.e) {
+			g_cache.e = e;
+			g_cache.dtype = dtype;
+			g_cache.m = m;
+			g_cache.n = n;
+			g_cache.opt = o;
+			e = nullptr;
+		}
+	}
 	delete e;
 	if (timing)
 		std::fprintf(stderr, "[b200lp] solve %lldx%lld: create %.1f ms, upload %.1f ms (copy %.1f), run %.1f ms (kernel %.1f), "
@@ -914,6 +986,19 @@ int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int
 	NEED(e);
 	if (!Acols || !b || !c) return fail(B200LP_ERR_ARG, "Acols, b, c must not be NULL");
 	return e->upload_columns(Acols, col0, ncols, b, c);
+}
+
+int b200lp_set_memory_cache(int32_t on) {
+	b200lp_engine* drop = nullptr;
+	int prev;
+	{
+		std::lock_guard<std::mutex> lk(g_cache.mu);
+		prev = g_cache.on ? 1 : 0;
+		g_cache.on = on != 0;
+		if (!g_cache.on) { drop = g_cache.e; g_cache.e = nullptr; }
+	}
+	delete drop;
+	return prev;
 }
 
 int b200lp_destroy(b200lp_engine* e) { delete e; return B200LP_OK; }

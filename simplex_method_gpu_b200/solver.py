@@ -101,6 +101,11 @@ def solve(A, b, c, eps: float = EPS, max_iter: int = MAX_ITER, dtype=None, devic
                     res.ms_upload, res.ms_solve, res.ms_download, res.kernel_launches, res.min_reduced_cost)
 
 
+def set_memory_cache(on: bool) -> bool:
+    """Keep the device buffers of the last solve() for the next call of the same shape (b200lp_set_memory_cache)."""
+    return bool(capi.lib().b200lp_set_memory_cache(1 if on else 0))
+
+
 class Engine:
     """Handle API: device state survives between calls (benchmark windows, phase tests)."""
 

@@ -89,6 +89,24 @@ def test_cli_reads_the_binary_twin_and_reports_parse_errors(lp, tmp_path):
     assert r.returncode == 1 and "Either failed to read m and n, or m > n." in r.stderr   # v4:403
 
 
+def test_memory_cache_reuses_the_engine_without_changing_results(lp, oracle):
+    A, b, c = oracle.gen_dense(300, 700, 2)
+    base = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    assert lp.set_memory_cache(True) is False
+    try:
+        for _ in range(3):                                   # same shape: the cached engine is reused
+            sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+            assert np.array_equal(sol.trace, base.trace) and np.array_equal(sol.x_b, base.x_b) and sol.z == base.z
+        A2, b2, c2 = oracle.gen_dense(64, 160, 3)            # another shape: a fresh engine replaces it
+        ref = oracle.solve(A2, b2, c2, eps=1e-9, max_iter=1 << 20, order=1)
+        sol = lp.solve(A2, b2, c2, eps=1e-9, max_iter=1 << 20)
+        assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.z == ref.z
+        sol = lp.solve(A, b, c, eps=1e-9, max_iter=7)         # other options: not reused either
+        assert sol.pivots == 7 and np.array_equal(sol.trace, base.trace[:7])
+    finally:
+        assert lp.set_memory_cache(False) is True
+
+
 def test_max_iter_and_unbounded(lp, oracle):
     A, b, c = lp.read_lp(os.path.join(GOLDEN, "sample.txt"), dtype=np.float64)
     for k in (1, 2, 3):
@@ -357,6 +375,12 @@ def test_non_identity_slack_block_is_priced_as_dense(lp, oracle):
         assert r["pivots"] == ref.pivots and int(r["status"]) == ref.status
         tr = e.trace()
         assert tr[:, 0].tolist() == ref.trace_p.tolist() and tr[:, 1].tolist() == ref.trace_q.tolist()
+    # the one-call solve() starts pivoting before its host-side check of the slack block has finished and must
+    # start over with all n columns as data when the block turns out not to be the identity
+    sol = lp.solve(A2, b, c, eps=1e-9, max_iter=50)
+    assert sol.pivots == ref.pivots and int(sol.status) == ref.status
+    assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist()
+    assert np.abs(sol.x_b - ref.x_b).max() <= 1e-9 * max(1.0, np.abs(ref.x_b).max())
 
 
 def test_device_generator_matches_oracle_generator(lp, oracle):
