@@ -206,7 +206,7 @@ public:
 		// priced and FTRAN'd as unit vectors and never stored.  The check reads m*m host elements (8.6 GB at
 		// m = 32768), so the structural columns are put on the wire first and the check runs on the host
 		// threads while the DMA engine works (pinned memory; a pageable copy simply finishes first).
-		if (opt.check_slack && n > m) {
+		if (opt.check_slack) {
 			CU(set_columns(n - m));
 			int rc = enqueue_block(A + (size_t)d.col0 * m, bv, cv);
 			if (rc) return rc;
@@ -842,7 +842,7 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	do {
 		t = Clk::now();
-		if (o.check_slack && n > m) {
+		if (o.check_slack) {
 			// optimistic: ship the structural columns and start pivoting; the m x m slack block (8.6 GB of host
 			// memory at m = 32768) is verified by host threads while the GPU works
 			if ((rc = e->upload_unchecked(A, b, c))) break;

@@ -235,7 +235,7 @@ def test_small_shape_fuzz_bit_exact(lp, oracle):
     seen = set()
     for case in range(60):
         m = int(rng.integers(1, 41))
-        n = m + int(rng.integers(0, 61))
+        n = m + (0 if case in (3, 17, 42) else int(rng.integers(0, 61)))    # n == m: nothing but the slack block
         ns = n - m
         A = np.zeros((m, n), order="F")
         A[:, :ns] = rng.uniform(-0.3 if case % 3 == 0 else 0.0, 1.0, (m, ns))
