@@ -58,3 +58,14 @@ def test_row_senses_are_converted(conv, tmp_path):
         q = tmp_path / "b.mps"
         q.write_text("NAME T\nROWS\n N COST\n L R0\nCOLUMNS\n X0 COST 1 R0 1\nRHS\n RHS R0 4\nBOUNDS\n UP BND X0 3\nENDATA\n")
         conv.read_mps(str(q))
+
+
+def test_text_binary_conversion(conv, engine_lib, tmp_path):
+    binf, txt = str(tmp_path / "s.b200lp"), str(tmp_path / "s.txt")
+    assert conv.main(["to-bin", os.path.join(GOLDEN, "sample.txt"), binf]) == 0
+    assert conv.main(["from-bin", binf, txt]) == 0
+    A0, b0, c0 = conv.read_text(os.path.join(GOLDEN, "sample.txt"))
+    A1, b1, c1 = conv.read_text(txt)
+    assert np.array_equal(A0, A1) and np.array_equal(b0, b1) and np.array_equal(c0, c1)
+    with open(binf, "rb") as f:
+        assert f.read(8) == b"B200LP1\0"

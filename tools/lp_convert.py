@@ -12,6 +12,8 @@ reads (`glp_read_mps(GLP_MPS_DECK)`), so the GLPK cross-check runs unchanged whe
   lp_convert.py to-mps   in.txt  out.mps     solver text (max c'x, Ax <= b, x >= 0, slack block last) -> fixed MPS
   lp_convert.py from-mps in.mps  out.txt     MPS (N/L/G/E rows, RHS, simple bounds rejected) -> solver text [A_s, I]
   lp_convert.py solve    in.txt|in.mps       HiGHS dual simplex, output in solver_glpk.cpp's format
+  lp_convert.py to-bin   in.txt  out.b200lp  solver text -> binary twin (include/b200lp_io.h; parsed by the library)
+  lp_convert.py from-bin in.b200lp out.txt   binary -> solver text (shortest round-trip decimals)
 
 MPS has no portable objective-sense record in the fixed format, so the objective row is written NEGATED
 (min -c'x) with a comment line saying so; `solve` and `from-mps` undo it (marker `* OBJSENSE MAX (negated)`).
@@ -161,7 +163,7 @@ def solve_highs(A, b, c):
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
-    for nm in ("to-mps", "from-mps"):
+    for nm in ("to-mps", "from-mps", "to-bin", "from-bin"):
         sp = sub.add_parser(nm)
         sp.add_argument("src")
         sp.add_argument("dst")
@@ -169,7 +171,11 @@ def main(argv=None):
     sp.add_argument("src")
     a = ap.parse_args(argv)
 
-    if a.cmd == "to-mps":
+    if a.cmd in ("to-bin", "from-bin"):
+        from simplex_method_gpu_b200.solver import read_lp_native, write_lp_native
+        A, b, c = read_lp_native(a.src, dtype=np.float64)          # reads either form (detected by the magic)
+        write_lp_native(a.dst, A, b, c, binary=a.cmd == "to-bin")
+    elif a.cmd == "to-mps":
         A, b, c = read_text(a.src)
         write_mps(a.dst, A, b, c, name=os.path.splitext(os.path.basename(a.src))[0].upper()[:8] or "B200LP")
     elif a.cmd == "from-mps":
