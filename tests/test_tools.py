@@ -69,3 +69,13 @@ def test_text_binary_conversion(conv, engine_lib, tmp_path):
     assert np.array_equal(A0, A1) and np.array_equal(b0, b1) and np.array_equal(c0, c1)
     with open(binf, "rb") as f:
         assert f.read(8) == b"B200LP1\0"
+
+
+def test_solve_with_engine_needs_a_gpu(conv, engine_lib, capsys):
+    import torch
+    rc = conv.main(["solve", os.path.join(GOLDEN, "sample.txt"), "--engine"])
+    out = capsys.readouterr()
+    if torch.cuda.is_available():
+        assert rc == 0 and out.out == "x[1] = 1\nx[2] = 3\nOptimal objective: 9\n"
+    else:
+        assert rc == 2 and "no CUDA device" in out.err          # no CPU fallback behind --engine

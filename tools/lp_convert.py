@@ -11,7 +11,8 @@ reads (`glp_read_mps(GLP_MPS_DECK)`), so the GLPK cross-check runs unchanged whe
 
   lp_convert.py to-mps   in.txt  out.mps     solver text (max c'x, Ax <= b, x >= 0, slack block last) -> fixed MPS
   lp_convert.py from-mps in.mps  out.txt     MPS (N/L/G/E rows, RHS, simple bounds rejected) -> solver text [A_s, I]
-  lp_convert.py solve    in.txt|in.mps       HiGHS dual simplex, output in solver_glpk.cpp's format
+  lp_convert.py solve    in.txt|in.mps [--engine]   HiGHS dual simplex (or, with --engine, the B200 engine in fp64),
+                                             output in solver_glpk.cpp's format, so the two can be diffed
   lp_convert.py to-bin   in.txt  out.b200lp  solver text -> binary twin (include/b200lp_io.h; parsed by the library)
   lp_convert.py from-bin in.b200lp out.txt   binary -> solver text (shortest round-trip decimals)
 
@@ -169,6 +170,7 @@ def main(argv=None):
         sp.add_argument("dst")
     sp = sub.add_parser("solve")
     sp.add_argument("src")
+    sp.add_argument("--engine", action="store_true", help="solve with libb200lp.so (needs a B200) instead of HiGHS")
     a = ap.parse_args(argv)
 
     if a.cmd in ("to-bin", "from-bin"):
@@ -190,7 +192,18 @@ def main(argv=None):
             A, b, c = mps_to_standard(*read_mps(a.src)[:5])
         else:
             A, b, c = read_text(a.src)
-        status, z, x = solve_highs(A, b, c)
+        if a.engine:
+            import simplex_method_gpu_b200 as lp
+            try:
+                sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 40, dtype=np.float64, trace_cap=1)
+            except lp.capi.B200LPError as exc:
+                print(exc, file=sys.stderr)
+                return 2
+            ns = split_slack(A, c)[0].shape[1]
+            status = {lp.SolveStatus.OptimumFound: 0, lp.SolveStatus.Unbounded: 3}.get(sol.status, 1)
+            z, x = sol.z, sol.x(A.shape[1])[:ns]
+        else:
+            status, z, x = solve_highs(A, b, c)
         if status != 0:
             print({2: "Problem has no feasible solution", 3: "Problem unbounded"}.get(status, f"HiGHS status {status}"))
             return 1
