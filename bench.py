@@ -9,9 +9,14 @@ a synthetic dense LP (oracle/lpgen_dense: A_s ~ U(0,1), b = (n_s/2)U(1,2),
 c_s ~ U(0.5,1.5), slack block last).  Default workload = the configuration
 BASELINE.json quotes its metric on: m=32768, n=65536, fp64 (fits one B200).
 
-  value ..... pivots/s with the LP resident in HBM (CUDA events on the engine's stream)
-  e2e ....... pivots/s through b200lp_solve_f64() with HOST buffers: per step the H2D of
-              the LP, the pivots and the D2H of the result are all inside the timed region
+  value ..... pivots/s with the LP resident in HBM (CUDA events on the engine's stream); same number
+              under device_loop, the like-for-like figure against the reference arm's device_loop
+  e2e ....... pivots/s through b200lp_solve_f64() with pinned HOST buffers: per step the cudaMalloc
+              of all device state, the H2D of the LP, the pivots, the D2H of the result and the
+              cudaFree are inside the timed region (what the reference's solve() does per call,
+              v4:245-271, 366-377); e2e_cached = the same with b200lp_set_memory_cache(1)
+  trace_sha256  sha256 of the int32 (p, q) trace of the last window: the same hash must come out of
+              every GPU count, of the reference arm and of tests/golden/trace_digests.json (CPU oracle)
   roofline .. algorithmic bytes per pivot 8*(2 m^2 + m (n-m)) / measured time, against
               the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (port of the reference loop) on the box's host cores,
@@ -19,11 +24,13 @@ BASELINE.json quotes its metric on: m=32768, n=65536, fp64 (fits one B200).
 
 --impl reference times the reference's own v4 CUDA solver (oracle/_ref, built from
 /root/reference by oracle/make_ref.sh with the documented minimal patches) on the same
-LP and window; when that library is unavailable it falls back to the CPU oracle port.
+LP and window, host buffers pinned like the reference's own main() (v4:408-414); when that
+library is unavailable it falls back to the CPU oracle port.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -46,11 +53,47 @@ SEED = 1
 EPS = 1e-9
 
 
+def config_for(name, m, n, P):
+    """The `config` object: key for key the same in both arms and at every GPU count."""
+    return {"workload": f"{name}: dense LP m={m} n={n} (n counts the slack block), seed {SEED}, "
+                        f"window of {P} pivots per step from the slack basis",
+            "m": m, "n": n, "pivots_per_step": P, "eps": EPS, "seed": SEED,
+            "l2": "working set (A_N + B^-1) larger than L2, no flush needed" if bytes_per_pivot(m, n) > 2 * 126e6 else
+                  "working set fits the 126 MB L2 (L2-resident; roofline fraction may exceed 1)"}
+
+
+def trace_digest(trace):
+    """sha256 over the little-endian int32 (p, q) rows of a pivot trace."""
+    a = np.ascontiguousarray(np.asarray(trace, dtype=np.int32).reshape(-1, 2)).astype("<i4")
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def golden_digest(name, P):
+    """Digest of the same window from the CPU oracle (tests/golden/trace_digests.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "trace_digests.json")) as f:
+            w = json.load(f)[name]["windows"][str(P)]
+        return w["trace_sha256"], w["z"]
+    except Exception:
+        return None, None
+
+
+def parity_fields(name, P, trace, z):
+    sha = trace_digest(trace)
+    gold, gz = golden_digest(name, P)
+    out = {"trace_sha256": sha, "trace_pivots": int(len(trace)), "z_after_window": float(z)}
+    if gold is not None:
+        out["trace_matches_golden"] = bool(sha == gold)
+        out["z_rel_diff_vs_golden"] = abs(z - gz) / max(1.0, abs(gz))
+    return out
+
+
 def profiled_traffic(workload, pivots_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the persistent kernel from the committed ncu capture
     (profiles/r01_traffic.json, written by tools/ncu_extract.py), scaled to this launch's pivot count."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        name = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             t = json.load(f)[workload]
         return t["dram_bytes_per_pivot"] * pivots_per_launch, t
     except Exception:
@@ -222,37 +265,43 @@ def run_b200_single(args, wl):
     value = pivots_timed / (total_ms * 1e-3)
     status_after = int(r["status"])
     grid = eng.grid_ctas
+    parity = parity_fields(args.workload, P, eng.trace(P), r["z"])
     eng.close()
 
     # ---- end to end through the C ABI with host buffers ("e2e")
-    e2e = None
+    e2e = e2e_cached = None
     if not args.no_e2e:
         A_pin = torch.empty((n, m), dtype=torch.float64, pin_memory=True)    # column-major m x n
         b_pin = torch.empty(m, dtype=torch.float64, pin_memory=True)
         c_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
         A_np = A_pin.numpy().T                                                # Fortran-ordered view
         lp.solver.lpgen_dense_into(A_pin.data_ptr(), b_pin.data_ptr(), c_pin.data_ptr(), m, n, 0, n, SEED)
-        times, piv = [], 0
-        # a caller that solves one LP after another keeps the device buffers between calls
-        # (b200lp_set_memory_cache): otherwise every call pays 40-500 ms of cudaMalloc / cudaFree for 16 GB
-        lp.set_memory_cache(True)
-        for s in range(args.warmup + args.steps):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            sol = lp.solve(A_np, b_pin.numpy(), c_pin.numpy(), eps=EPS, max_iter=P, device=dev, trace_cap=1)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            if s >= args.warmup:
-                times.append(dt)
-                piv += sol.pivots
-        lp.set_memory_cache(False)
+        def timed_calls(cached):
+            # cached: a caller that solves one LP after another keeps the device buffers between calls
+            # (b200lp_set_memory_cache); default / headline: like the reference, every call allocates and
+            # frees all device state (v4:245-264, 370-377)
+            lp.set_memory_cache(cached)
+            times, piv, sol = [], 0, None
+            for s_ in range(args.warmup + args.steps):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                sol = lp.solve(A_np, b_pin.numpy(), c_pin.numpy(), eps=EPS, max_iter=P, device=dev, trace_cap=P)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                if s_ >= args.warmup:
+                    times.append(dt)
+                    piv += sol.pivots
+            lp.set_memory_cache(False)
+            return {"value": piv / sum(times), "unit": "pivots/s", "ms_per_step": 1e3 * sum(times) / len(times),
+                    "last_ms": {"upload": sol.ms_upload, "solve": sol.ms_solve, "download": sol.ms_download},
+                    "trace_sha256": trace_digest(sol.trace)}
+        plain, cached = timed_calls(False), timed_calls(True)
         h2d = 8 * (m * (n - m) + m + n)         # dense columns + b + c (the slack block is verified on the host, not copied)
-        d2h = 8 * m + 4 * m + 64                # x_b, b_ixs, result block
-        e2e = {"value": piv / sum(times), "unit": "pivots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * sum(times) / len(times), "pivots_per_step": P,
-               "last_ms": {"upload": sol.ms_upload, "solve": sol.ms_solve, "download": sol.ms_download},
-               "note": "b200lp_solve_f64 per step with pinned host buffers; device buffers kept between calls "
-                       "(b200lp_set_memory_cache(1)); every step still uploads the whole LP and downloads the result"}
+        d2h = 8 * m + 4 * m + 8 * P + 64        # x_b, b_ixs, trace, result block
+        e2e = {**plain, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "pivots_per_step": P,
+               "note": "b200lp_solve_f64 per step with pinned host buffers, memory cache OFF (default): cudaMalloc of all "
+                       "device state, H2D of the LP, the pivots, D2H of x_b / b_ixs / trace and cudaFree inside the timed region"}
+        e2e_cached = {**cached, "note": "same call with b200lp_set_memory_cache(1): device buffers survive between calls"}
         del A_np, A_pin
 
     peak, peak_src = measured_peak_gbs()
@@ -263,16 +312,13 @@ def run_b200_single(args, wl):
         "metric": "pivots/s, dense revised simplex (fp64)", "value": value, "unit": "pivots/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: dense LP m={m} n={n} (n counts the slack block), seed {SEED}, "
-                               f"window of {P} pivots per step from the slack basis",
-                   "m": m, "n": n, "pivots_per_step": P, "eps": EPS, "grid_ctas": grid,
-                   "l2": "working set (A_N + B^-1) larger than L2, no flush needed" if bpp > 2 * 126e6 else
-                         "working set fits the 126 MB L2 (L2-resident; roofline fraction may exceed 1)",
-                   "parallelism": "1 GPU, persistent cooperative kernel"},
+        "config": config_for(args.workload, m, n, P),
+        "engine": {"grid_ctas": grid, "parallelism": "1 GPU, persistent cooperative kernel"},
+        "device_loop": {"value": value, "unit": "pivots/s", "note": "CUDA events around the pivot loop only (= value)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_pivot": bpp,
                      "bytes_per_launch": bpp * P, "kernel": "simplex_persistent<double>"},
-        "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "e2e_cached": e2e_cached, **parity,
         "status_after": status_after, "pivots_timed": int(pivots_timed), "engine_event_ms": internal_ms,
     }
     return out
@@ -298,14 +344,29 @@ def cpu_baseline(wl, budget_s=20.0):
 
 # ---------------------------------------------------------------- reference arm
 
-def run_reference(args, wl):
-    """The reference's own v4 CUDA solver on the same LP; falls back to the CPU port."""
+def _pinned_lp(m, n):
+    """Host buffers for the reference arm: pinned like the reference's own main() allocates them (cudaMallocHost,
+    v4:408-414) when torch + CUDA are there, pageable numpy otherwise.  Returns (A col-major m x n, b, c, pinned?)."""
     import oracle
-    m, n, P = wl["m"], wl["n"], args.pivots or wl["pivots"]
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None
-    A, b, c = oracle.gen_dense(m, n, SEED)
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA")
+        A_pin = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+        b_pin = torch.empty(m, dtype=torch.float64, pin_memory=True)
+        c_pin = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        oracle.gen_dense_into(A_pin.data_ptr(), b_pin.data_ptr(), c_pin.data_ptr(), m, n, SEED)
+        return A_pin.numpy().T, b_pin.numpy(), c_pin.numpy(), True, (A_pin, b_pin, c_pin)
+    except Exception:
+        A, b, c = oracle.gen_dense(m, n, SEED)
+        return A, b, c, False, None
+
+
+def reference_workload(args, name, wl, P):
+    """One workload on the reference's own v4 CUDA solve() (or the CPU port): per step one call from the slack basis
+    with host buffers in / out, like main() calls it (v4:423)."""
+    import oracle
+    m, n = wl["m"], wl["n"]
     use_v4 = oracle.ref_available(np.float64) and not args.ref_cpu
     if use_v4:
         try:
@@ -313,46 +374,109 @@ def run_reference(args, wl):
             use_v4 = torch.cuda.is_available()
         except Exception:
             use_v4 = False
-    times, piv, loop_s = [], 0, 0.0
-    kind = "reference"
+    times, piv, loop_s, r = [], 0, 0.0, None
     if use_v4:
-        P_ref = min(P, args.ref_pivots or P)
+        A, b, c, pinned, keep = _pinned_lp(m, n)
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            r = oracle.ref_solve(A, b, c, eps=EPS, max_iter=P_ref, trace_cap=1)
+            r = oracle.ref_solve(A, b, c, eps=EPS, max_iter=P, trace_cap=P, always_readback=True)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
                 piv += r.pivots
                 loop_s += r.secs_loop
+        kind, cores = "reference-gpu", 1
         sample = (f"reference v4 CUDA solve() (oracle/_ref/libv4ref_f64.so: fp64 retarget + init-grid/length/pointer-mode "
-                  f"fixes) on the B200, {P_ref} iterations per step from the slack basis, host buffers in/out")
-        cores = 1
-        extra = {"device_loop_pivots_per_s": piv / loop_s if loop_s > 0 else None, "runs_on": "B200 (cuBLAS + CUB)"}
+                  f"fixes, make_ref.sh P1-P8) on the B200, {P} iterations per step from the slack basis, "
+                  f"{'pinned' if pinned else 'pageable'} host buffers in/out, cudaMalloc/cudaFree per call (v4:245-264, 370-377); "
+                  f"1 host thread drives the GPU")
+        extra = {"device_loop": {"value": piv / loop_s if loop_s > 0 else None, "unit": "pivots/s",
+                                 "note": "host clock from after the init kernels (v4:283) to before the frees (v4:370), "
+                                         "i.e. the loop plus the final read-back"},
+                 "runs_on": "B200 (cuBLAS + CUB)", "host_buffers": "pinned" if pinned else "pageable"}
+        del keep
     else:
-        kind = "port"
-        P_ref = min(P, args.ref_pivots or 8)
+        A, b, c = oracle.gen_dense(m, n, SEED)
+        P = min(P, args.ref_pivots or 8)
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            r = oracle.solve(A, b, c, eps=EPS, max_iter=P_ref, trace_cap=1)
+            r = oracle.solve(A, b, c, eps=EPS, max_iter=P, trace_cap=P)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
                 piv += r.pivots
-        cores = oracle.num_threads()
-        sample = f"CPU oracle port, {P_ref} iterations per step from the slack basis, {cores} OpenMP threads"
-        extra = {"runs_on": "host CPU"}
+        kind, cores = "port", oracle.num_threads()
+        sample = f"CPU oracle port, {P} iterations per step from the slack basis, {cores} OpenMP threads"
+        extra = {"device_loop": None, "runs_on": "host CPU", "host_buffers": "pageable"}
     value = piv / sum(times)
-    return {
-        "impl": "reference", "metric": "pivots/s, dense revised simplex (fp64)", "value": value, "unit": "pivots/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: dense LP m={m} n={n}, seed {SEED}, {P_ref} pivots per step", "m": m, "n": n,
-                   "pivots_per_step": P_ref, "eps": EPS},
-        "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        **extra,
-    }
+    trace = np.stack([r.trace_p, r.trace_q], axis=1) if len(r.trace_p) else np.zeros((0, 2), np.int32)
+    return {"value": value, "unit": "pivots/s", "ms_per_step": 1e3 * sum(times) / len(times),
+            "config": config_for(name, m, n, P),
+            "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            **parity_fields(name, P, trace, r.z), **extra}
+
+
+def run_reference(args, wl):
+    """The reference's own v4 CUDA solver on the same LP (rank 0 only); falls back to the CPU port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    P = args.pivots or wl["pivots"]
+    main_ = reference_workload(args, args.workload, wl, P)
+    out = {"impl": "reference", "metric": "pivots/s, dense revised simplex (fp64)", "value": main_["value"],
+           "unit": "pivots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": main_["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic"}
+    out.update({k: v for k, v in main_.items() if k not in ("value", "unit", "ms_per_step")})
+    extra = {}
+    if args.gpus == 1:
+        for name in [x for x in args.extras.split(",") if x and x != args.workload]:
+            r = reference_workload(args, name, WORKLOADS[name], WORKLOADS[name]["pivots"])
+            extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "config", "device_loop", "trace_sha256",
+                                             "z_after_window", "trace_matches_golden") if k in r}
+    if extra:
+        out["extra"] = extra
+    return out
+
+
+# ---------------------------------------------------------------- CPU baselines of the smaller named configs (SURVEY 8(d3))
+
+def cpu_extras(budget_s=20.0):
+    """Rank 0, N=1 only: the CPU port on C2 (whole solve) and on a window of C3, and HiGHS dual simplex
+    (scipy `highs-ds`, 1 thread — the stand-in for solver_glpk.cpp's glp_simplex, GLPK being absent) time-to-optimal on C2."""
+    import oracle
+    out = {}
+    m, n = WORKLOADS["C2"]["m"], WORKLOADS["C2"]["n"]
+    A, b, c = oracle.gen_dense(m, n, SEED)
+    t0 = time.perf_counter()
+    s = oracle.solve(A, b, c, eps=EPS, max_iter=1 << 30, trace_cap=1)
+    dt = time.perf_counter() - t0
+    out["C2_cpu_port_to_optimal"] = {"seconds": dt, "pivots": int(s.pivots), "pivots_per_s": s.pivots / dt, "z": s.z,
+                                     "status": int(s.status), "cores": oracle.num_threads(), "kind": "port"}
+    try:
+        from scipy.optimize import linprog
+        t0 = time.perf_counter()
+        r = linprog(-c[:n - m], A_ub=A[:, :n - m], b_ub=b, method="highs-ds")
+        dt = time.perf_counter() - t0
+        out["C2_highs_ds_to_optimal"] = {"seconds": dt, "iterations": int(r.nit), "z": float(-r.fun), "status": int(r.status),
+                                         "cores": 1, "rel_diff_vs_port": abs(-r.fun - s.z) / abs(s.z),
+                                         "note": "scipy.optimize.linprog(method='highs-ds'); GLPK (solver_glpk.cpp:23) is not installed"}
+    except Exception as exc:
+        out["C2_highs_ds_to_optimal"] = {"unavailable": str(exc)}
+    m, n = WORKLOADS["C3"]["m"], WORKLOADS["C3"]["n"]
+    A, b, c = oracle.gen_dense(m, n, SEED)
+    k, done, t_used = 8, 0, 0.0
+    while True:
+        t0 = time.perf_counter()
+        s = oracle.solve(A, b, c, eps=EPS, max_iter=k, trace_cap=1)
+        t_used, done = time.perf_counter() - t0, s.pivots
+        if t_used > budget_s / 3 or s.status != oracle.MAX_ITER:
+            break
+        k *= 4
+    out["C3_cpu_port_window"] = {"seconds": t_used, "pivots": int(done), "pivots_per_s": done / t_used,
+                                 "cores": oracle.num_threads(), "kind": "port"}
+    return out
 
 
 def main():
@@ -365,7 +489,7 @@ def main():
     ap.add_argument("--pivots", type=int, default=0, help="pivots per step (0 = workload default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extras", default="C3", help="comma list of extra single-GPU workloads reported under 'extra'")
+    ap.add_argument("--extras", default="C2,C3", help="comma list of extra single-GPU workloads reported under 'extra' (both arms)")
     ap.add_argument("--tto", default="C2,C3", help="comma list of workloads solved to optimality (time-to-optimal), '' = none")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU port")
     ap.add_argument("--ref-pivots", type=int, default=0)
@@ -389,11 +513,14 @@ def main():
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wl)
         extra = {}
+        if not args.no_cpu:
+            extra["cpu"] = cpu_extras()
         for name in [x for x in args.extras.split(",") if x and x != args.workload]:
             sub = argparse.Namespace(**vars(args))
             sub.workload, sub.pivots, sub.no_e2e = name, 0, True
             r = run_b200_single(sub, WORKLOADS[name])
-            extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "roofline", "config", "clocks", "gpu_launches")}
+            extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "roofline", "config", "device_loop", "clocks",
+                                             "gpu_launches", "trace_sha256", "z_after_window", "trace_matches_golden") if k in r}
         tto = {}
         for name in [x for x in args.tto.split(",") if x]:
             tto[name] = time_to_optimal(name, WORKLOADS[name], int(os.environ.get("LOCAL_RANK", "0")))

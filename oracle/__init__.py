@@ -127,6 +127,12 @@ def gen_dense(m: int, n: int, seed: int = 1, dtype=np.float64):
     return A, b, c
 
 
+def gen_dense_into(A_ptr: int, b_ptr: int, c_ptr: int, m: int, n: int, seed: int = 1, dtype=np.float64):
+    """Same LP written into caller-owned host memory (e.g. pinned buffers): A column-major m x n, b (m), c (n)."""
+    fn = lib().lpgen_dense_f64 if np.dtype(dtype) == np.float64 else lib().lpgen_dense_f32
+    fn(C.c_void_p(A_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), m, n, seed)
+
+
 def gen_klee_minty(d: int):
     A = np.empty((d, 2 * d), np.float64, order="F")
     b = np.empty(d, np.float64)
@@ -164,8 +170,11 @@ def build_ref() -> bool:
     src = "/root/reference/src/v4_cub_reduction.cu"
     if not os.path.exists(src):
         return ref_available()
-    outs = [os.path.join(_REF_DIR, f) for f in ("libv4ref_f64.so", "libv4ref_f32.so", "v4_stock.out")]
-    deps = [src, os.path.join(_HERE, "make_ref.sh"), os.path.join(_HERE, "ref_harness.cu")]
+    outs = [os.path.join(_REF_DIR, f) for f in ("libv4ref_f64.so", "libv4ref_f32.so", "v4_stock.out", "v4_shim.out",
+                                                "v4_shim_env_f64.out", "v4_shim_env_f32.out", "v4_cli_f64.out", "v4_cli_f32.out")]
+    deps = [src, os.path.join(_HERE, "make_ref.sh"), os.path.join(_HERE, "ref_harness.cu"), os.path.join(_HERE, "v4_shim.cu"),
+            os.path.join(_HERE, "ref_cli.cu"), os.path.join(os.path.dirname(_HERE), "integration", "v4_b200.inc"),
+            os.path.join(os.path.dirname(_HERE), "include", "b200lp.h")]
     if all(os.path.exists(o) for o in outs) and min(map(os.path.getmtime, outs)) > max(map(os.path.getmtime, deps)):
         return True
     subprocess.run([os.path.join(_HERE, "make_ref.sh")], check=True, capture_output=True)
@@ -182,6 +191,12 @@ def ref_stock_binary() -> str | None:
     return p if os.path.exists(p) else None
 
 
+def ref_binary(name: str) -> str | None:
+    """v4_shim.out (stock main() + the INTEGRATION.md binding), v4_shim_env_f{32,64}.out, v4_cli_f{32,64}.out."""
+    p = os.path.join(_REF_DIR, name)
+    return p if os.path.exists(p) else None
+
+
 def _ref_lib(dtype):
     dt = np.dtype(dtype)
     if dt not in _ref_libs:
@@ -193,6 +208,8 @@ def _ref_lib(dtype):
                                 C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_sizeof_real.restype = C.c_int
         assert L.ref_sizeof_real() == dt.itemsize
+        L.ref_set_always_readback.restype = None
+        L.ref_set_always_readback.argtypes = [C.c_int]
         _ref_libs[dt] = L
     return _ref_libs[dt]
 
@@ -211,13 +228,17 @@ class RefSolution:
     secs_loop: float
 
 
-def ref_solve(A, b, c, eps=1e-4, max_iter=5, trace_cap=None) -> RefSolution:
-    """The reference's own solve() (v4:219, patched per make_ref.sh) on the current CUDA device."""
+def ref_solve(A, b, c, eps=1e-4, max_iter=5, trace_cap=None, always_readback=False) -> RefSolution:
+    """The reference's own solve() (v4:219, patched per make_ref.sh) on the current CUDA device.
+    `always_readback`: also return z / x_b / b_ixs when the run stops at max_iter (patch P8; v4:363 reads them
+    back on OptimumFound only).  Arrays are passed as they are (no copy when already column-major of one dtype),
+    so pinned host buffers stay pinned like the reference's own cudaMallocHost arrays (v4:408-414)."""
     dt = np.dtype(A.dtype)
     A = np.asfortranarray(A, dtype=dt)
     b = np.ascontiguousarray(b, dtype=dt)
     c = np.ascontiguousarray(c, dtype=dt)
     m, n = A.shape
+    _ref_lib(dt).ref_set_always_readback(1 if always_readback else 0)
     cap = int(trace_cap if trace_cap is not None else min(max_iter, 1 << 22))
     x_b = np.zeros(m, dt)
     b_ixs = np.zeros(m, np.int32)

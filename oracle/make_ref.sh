@@ -5,6 +5,10 @@
 #   _ref/v4_stock.out       src/v4_cub_reduction.cu exactly as shipped, Makefile flags + -arch
 #   _ref/libv4ref_f64.so    v4 + the minimal patch list below, real = double
 #   _ref/libv4ref_f32.so    same patches, real = float
+#   _ref/v4_cli_f{32,64}.out the patched copy as a program with its own main() (V4_EPS / V4_MAX_ITER from the environment)
+#   _ref/v4_shim.out        the STOCK source with only solve() (v4:219-380) cut out + integration/v4_b200.inc + -lb200lp:
+#                           the reference's unmodified main() driving the B200 engine
+#   _ref/v4_shim_env_f{32,64}.out  the same on the patched copy (run-time EPS / MAX_ITER), for LPs beyond 5 iterations
 #
 # Patch list (every item except P1 is arithmetic-neutral):
 #   P1 real = double and cublasS* -> cublasD*                     (v4:12, 289..365)   [f64 only]
@@ -17,6 +21,8 @@
 #      (v4:289-290, 307-308, 333 pass host stack addresses)
 #   P6 pivot-trace hook after the q read-back (v4:325), iteration count export,
 #      "# Iteration" printing silenced (v4:287)
+#   P8 z / x_b / b_ixs read back for every status when ref_always_readback is set (v4:363 does it on
+#      OptimumFound only); the same cublasDdot + two copies, after the loop, so the loop is untouched
 #   P7 64-bit sizes and element offsets (v4:33, 60, 77, 86, 246, 248, 269, 308): the shipped
 #      `int` products m*n, (m+1)*n and p*m overflow at m = 32768, n = 65536 (config C4)
 set -euo pipefail
@@ -59,6 +65,7 @@ patch_src() { # $1 = S|D  $2 = out file
 		-e '308s/&one/d_one/; 308s/&zero/d_zero/' \
 		-e '333s/&one/d_one/' \
 		-e '325s/$/ if (i < ref_trace_cap) { ref_trace[2 * i] = p; ref_trace[2 * i + 1] = q; }/' \
+		-e '363s/if \(status == SolveStatus::OptimumFound\)/if (status == SolveStatus::OptimumFound || ref_always_readback)/' \
 		-e '360s/$/ ref_iterations = (status == SolveStatus::MaxIter) ? i : i + 1; cudaFree(d_one); cudaFree(d_zero);/' \
 		"$SRC" > "$2"
 	if [ "$1" = "D" ]; then
@@ -70,6 +77,7 @@ patch_src() { # $1 = S|D  $2 = out file
 		&& grep -q 'ref_trace\[2 \* i\]' "$2" && grep -q 'ref_iterations =' "$2" \
 		&& grep -q 'if (!ref_quiet)' "$2" && grep -q 'd_c_b, m, cudaMemcpyDeviceToDevice' "$2" \
 		&& [ "$(grep -c 'BS_2D - 1' "$2")" = "2" ] && [ "$(grep -c '(long long)' "$2")" -ge 4 ] \
+ 		&& grep -q 'ref_always_readback)' "$2" \
 		&& grep -q 'long long R2C' "$2" && grep -q 'long long size;' "$2" || { echo "make_ref: patch did not apply cleanly" >&2; exit 1; }
 }
 
@@ -80,4 +88,27 @@ for V in D S; do
 	$NVCC --std=c++20 $ARCH -O2 -shared -Xcompiler -fPIC -DREF_SOURCE="\"$P\"" "$HERE/ref_harness.cu" \
 		-o "$OUT/$NAME" -ccbin "$CCBIN" -lcublas
 done
+
+# ---- the drop-in, compiled: reference main() + integration/v4_b200.inc + libb200lp.so (no cuBLAS on the link line)
+ROOT="$(cd "$HERE/.." && pwd)"
+LIBDIR="$ROOT/simplex_method_gpu_b200"
+cut_solve() { # $1 = source, $2 = out: v4:219-380 (the old solve()) replaced by its forward declaration
+	sed -E -e '219,380d' "$1" | sed -e '218a\
+std::pair<real, SolveStatus> solve(real* A, real* b, real* c, real* x_b, int* b_ixs, int m, int n, TimeStruct\& t);' > "$2"
+	grep -q 'TimeStruct& t);' "$2" && ! grep -q 'cublasCreate' "$2" && grep -q 'int main(int argc' "$2" \
+		|| { echo "make_ref: cutting solve() out did not apply cleanly" >&2; exit 1; }
+}
+if [ -f "$LIBDIR/libb200lp.so" ]; then
+	LINK="-I$ROOT/include -L$LIBDIR -lb200lp -Xlinker -rpath -Xlinker \$ORIGIN/../../simplex_method_gpu_b200"
+	cut_solve "$SRC" "$TMP/v4_cut_stock.cu"
+	$NVCC --std=c++20 $ARCH -DREF_SOURCE="\"$TMP/v4_cut_stock.cu\"" "$HERE/v4_shim.cu" -o "$OUT/v4_shim.out" -ccbin "$CCBIN" $LINK
+	for V in D S; do
+		if [ "$V" = "D" ]; then SFX=f64; else SFX=f32; fi
+		cut_solve "$TMP/v4_patched_$V.cu" "$TMP/v4_cut_$V.cu"
+		$NVCC --std=c++20 $ARCH -DREF_ENV -DREF_SOURCE="\"$TMP/v4_cut_$V.cu\"" "$HERE/v4_shim.cu" -o "$OUT/v4_shim_env_$SFX.out" -ccbin "$CCBIN" $LINK
+		$NVCC --std=c++20 $ARCH -O2 -DREF_SOURCE="\"$TMP/v4_patched_$V.cu\"" "$HERE/ref_cli.cu" -o "$OUT/v4_cli_$SFX.out" -ccbin "$CCBIN" -lcublas
+	done
+else
+	echo "make_ref: libb200lp.so not built yet, skipping the drop-in binaries" >&2
+fi
 ls -la "$OUT"

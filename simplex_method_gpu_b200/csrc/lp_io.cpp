@@ -71,11 +71,11 @@ template <typename T>
 struct Sink {
 	T *A, *b, *c;
 	int64_t m, n;
-	inline void put(int64_t k, double v) const {
+	inline void put(int64_t k, T v) const {
 		const int64_t mn = m * n;
-		if (k < mn) A[(size_t)(k / n) + (size_t)(k % n) * (size_t)m] = (T)v;     // row-major text -> column-major (v4:98)
-		else if (k < mn + m) b[k - mn] = (T)v;
-		else c[k - mn - m] = (T)v;
+		if (k < mn) A[(size_t)(k / n) + (size_t)(k % n) * (size_t)m] = v;     // row-major text -> column-major (v4:98)
+		else if (k < mn + m) b[k - mn] = v;
+		else c[k - mn - m] = v;
 	}
 };
 
@@ -146,13 +146,21 @@ int parse_text(const char* txt, size_t len, int32_t dtype, bool pinned, b200lp_p
 			while (q < e && is_space(*q)) ++q;
 			if (q >= e) break;
 			if (*q == '+') ++q;                    // operator>> accepts a leading '+', from_chars does not
-			double v;
+			// parsed in the problem's own scalar type: the decimal is rounded ONCE, like the reference's
+			// operator>>(real) (v4:94-104); going through double first can be 1 ulp off in float
+			T v;
 			auto r = std::from_chars(q, e, v);
 			if (r.ptr == q || r.ec == std::errc::invalid_argument) { bad[t] = k; break; }
-			if (r.ec == std::errc::result_out_of_range) v = std::strtod(std::string(q, r.ptr).c_str(), nullptr);
+			if (r.ec == std::errc::result_out_of_range) {
+				const std::string tok(q, r.ptr);
+				v = sizeof(T) == 8 ? (T)std::strtod(tok.c_str(), nullptr) : (T)std::strtof(tok.c_str(), nullptr);
+			}
 			sink.put(k, v);
 			++k;
 			q = r.ptr;
+			// "1.5abc": operator>> takes the 1.5 and fails on the next extraction; a token that is not
+			// consumed to its end therefore fails at the FOLLOWING index (and never shifts later indices)
+			if (q < e && !is_space(*q)) { bad[t] = k; break; }
 		}
 	});
 	int64_t got = std::min<int64_t>(ntok[nt], need);

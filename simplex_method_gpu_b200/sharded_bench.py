@@ -59,6 +59,7 @@ def run(args, wl, seed, eps):
     total_ms = float(t_ms.sum().item())
     value = piv / (total_ms * 1e-3)
     x_b, b_ixs, _ = eng.download()
+    trace = eng.trace(P)
     digest = torch.tensor([float(r["pivots"]), float(r["z"]), float(np.asarray(b_ixs, np.float64).sum())],
                           dtype=torch.float64, device="cuda")
     lo, hi = digest.clone(), digest.clone()
@@ -93,9 +94,17 @@ def run(args, wl, seed, eps):
                "h2d_bytes_per_step": 8 * (m * (n - m) + world * (m + n)), "d2h_bytes_per_step": world * (12 * m + 64),
                "ms_per_step": 1e3 * sum(times) / len(times), "pivots_per_step": P,
                "note": "each rank uploads its own column block of A (and b, c) from pinned host memory through "
-                       "b200lp_upload_columns, runs the window and reads x_b / b_ixs back"}
+                       "b200lp_upload_columns, runs the window and reads x_b / b_ixs back; device buffers are kept "
+                       "between steps (handle API) — compare with the single-GPU arm's e2e_cached"}
 
-    from bench import bytes_per_pivot, measured_peak_gbs
+    from bench import bytes_per_pivot, config_for, measured_peak_gbs, parity_fields
+    # every rank holds the replicated trace: all of them must carry the digest rank 0 prints
+    sha_bytes = torch.tensor(list(bytes.fromhex(parity_fields(args.workload, P, trace, r["z"])["trace_sha256"])),
+                             dtype=torch.int32, device="cuda")
+    lo_s, hi_s = sha_bytes.clone(), sha_bytes.clone()
+    dist.all_reduce(lo_s, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_s, op=dist.ReduceOp.MAX)
+    replicas_agree = replicas_agree and bool(torch.equal(lo_s, hi_s))
     peak, peak_src = measured_peak_gbs()
     bpp = bytes_per_pivot(m, n)
     achieved = bpp * piv / (total_ms * 1e-3) / 1e9
@@ -103,16 +112,16 @@ def run(args, wl, seed, eps):
         "metric": "pivots/s, dense revised simplex (fp64)", "value": value, "unit": "pivots/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: dense LP m={m} n={n} (n counts the slack block), seed {seed}, "
-                               f"window of {P} pivots per step from the slack basis",
-                   "m": m, "n": n, "pivots_per_step": P, "eps": eps, "grid_ctas": eng.grid_ctas,
-                   "l2": "per-GPU working set larger than L2" if bpp / world > 2 * 126e6 else "per-GPU working set near/below L2 size",
-                   "parallelism": f"{world} GPUs: B^-1 row-sharded, A column-sharded, peer-store exchanges (no NCCL on the data path)"},
+        "config": config_for(args.workload, m, n, P),
+        "engine": {"grid_ctas": eng.grid_ctas,
+                   "parallelism": f"{world} GPUs: B^-1 row-sharded, A column-sharded, peer-store exchanges (no NCCL on the data path)",
+                   "l2": "per-GPU working set larger than L2" if bpp / world > 2 * 126e6 else "per-GPU working set near/below L2 size"},
+        "device_loop": {"value": value, "unit": "pivots/s", "note": "CUDA events around the pivot loop only, max over ranks (= value)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                      "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
                      "bytes_per_pivot": bpp, "kernel": "simplex_persistent_sharded<double>"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e,
-        "replicas_agree": replicas_agree, "pivots_timed": int(piv),
+        "replicas_agree": replicas_agree, "pivots_timed": int(piv), **parity_fields(args.workload, P, trace, r["z"]),
         "exchange_bytes_per_pivot_per_rank": plan.exchange_bytes_per_pivot(),
     }
     eng.close()

@@ -258,6 +258,26 @@ def lpgen_dense(m, n, seed=1, dtype=np.float64):
 
 # ---------------------------------------------------------------- text format + printing
 
+def _round_once_f32(tok: str, x: float) -> np.float32:
+    """Decimal token -> float32 rounded ONCE, like the reference's ``operator>>(float)`` (v4:94-104).  ``x`` is the
+    correctly rounded double of the token; casting it is wrong only when it sits exactly on the midpoint of two
+    neighbouring floats while the decimal itself does not — decided with exact rational arithmetic."""
+    f = np.float32(x)
+    if not np.isfinite(f) or float(f) == x:
+        return f
+    other = np.nextafter(f, np.float32(np.inf) if x > float(f) else np.float32(-np.inf))
+    if not np.isfinite(other) or (float(f) + float(other)) / 2 != x:
+        return f
+    try:
+        from fractions import Fraction
+        exact, mid = Fraction(tok), Fraction(x)
+    except (ValueError, ZeroDivisionError):
+        return f
+    if exact == mid:
+        return f                                    # a true tie: round-half-even already applied by the cast
+    return f if (exact < mid) == (float(f) < float(other)) else other
+
+
 def read_lp(path_or_file, dtype=REAL):
     """Parse the reference's LP text format (v4:401-420, input/sample.txt): ``m n``,
     A as m rows of n numbers, b (m), c (n); anything after that is ignored."""
@@ -287,7 +307,10 @@ def read_lp(path_or_file, dtype=REAL):
         if k < m * n + m:
             raise ValueError(f"Failed to read ({k - m * n},0) for b")
         raise ValueError(f"Failed to read (0,{k - m * n - m}) for c")
-    v = np.asarray(vals, dtype=np.float64)
+    if np.dtype(dtype) == np.float32:
+        v = np.array([_round_once_f32(t, x) for t, x in zip(toks[2:2 + need], vals)], dtype=np.float32)
+    else:
+        v = np.asarray(vals, dtype=np.float64)
     A = np.asfortranarray(v[:m * n].reshape(m, n), dtype=dtype)              # row-major text -> col-major
     b = v[m * n:m * n + m].astype(dtype)
     c = v[m * n + m:].astype(dtype)
