@@ -66,12 +66,17 @@ typedef struct {
 	int32_t l2_persist_mb; /* pin the head of B^-1 in the persisting part of L2: -1 = off (default), 0 = as much as
 	                          the device allows, else MiB */
 	int32_t price_mode;   /* 0 = auto (register-staged loads up to a 2 GB A shard, TMA ring above), 1 = TMA ring, 2 = register-staged */
-	int32_t reserved;
+	int32_t ratio_group_rows; /* rows of B^-1 whose ratio test runs as one unit inside the update+FTRAN pass: 0 = auto (256) */
+	double  pivot_tol;    /* ratio-test eligibility alpha > pivot_tol; 0 (default) = the reference's strict test (v4:203) */
+	int32_t price_tail;   /* columns at the end of a pricing pass handed out one at a time: 0 = auto, -1 = none, else count */
+	int32_t fuse_book2;   /* x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass (3 grid barriers per
+	                         pivot instead of 4): 0 = auto (when y fits in shared memory), -1 = off */
+	int32_t reserved[4];
 } b200lp_options;
 
 typedef struct {
 	int32_t status;       /* B200LP_STATUS_* */
-	int32_t reserved;
+	int32_t aborted;      /* 1: the run ended early because of b200lp_abort() (status stays MAX_ITER) */
 	int64_t iterations;   /* number of "# Iteration k" lines the reference prints (v4:287) */
 	int64_t pivots;
 	double  z;            /* c_b . x_b (v4:365) */
@@ -99,6 +104,19 @@ int b200lp_solve_f32(const float* A, const float* b, const float* c, int64_t m, 
 		const b200lp_options* opt, float* x_b, int32_t* b_ixs,
 		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
 
+/*
+ * The same call over several GPUs of one box (`devices, ndev`): one process, one persistent kernel
+ * per device, B^-1 row-sharded and A column-sharded across them, peer access instead of CUDA IPC.  `devices` lists
+ * ndev CUDA ordinals (1..8).  A device may be repeated: its ranks then share one cooperative launch (used by the
+ * tests on single-GPU boxes; it buys no speed).  Results are bit-identical to the single-GPU call.
+ */
+int b200lp_solve_f64_multi(const double* A, const double* b, const double* c, int64_t m, int64_t n,
+		const b200lp_options* opt, const int32_t* devices, int32_t ndev, double* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
+int b200lp_solve_f32_multi(const float* A, const float* b, const float* c, int64_t m, int64_t n,
+		const b200lp_options* opt, const int32_t* devices, int32_t ndev, float* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res);
+
 /* Keep the device buffers of the last b200lp_solve_* call for the next call of the same shape, dtype and options
  * (on != 0), or release them and go back to the reference's behaviour of leaving nothing behind (on == 0, the
  * default).  Creating and freeing 16 GB of device memory costs 40-500 ms per call at m = 32768.  Returns the
@@ -109,6 +127,10 @@ int b200lp_set_memory_cache(int32_t on);
 
 /* allocates A_N, B^-1 and all vectors for an m x n problem (v4:245-264) */
 int b200lp_create(int32_t dtype, int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out);
+/* the same engine spread over ndev GPUs of this process (see b200lp_solve_f64_multi); every handle call below
+ * works on it except the per-phase entry points and the IPC calls */
+int b200lp_create_multi(int32_t dtype, int64_t m, int64_t n, const int32_t* devices, int32_t ndev,
+		const b200lp_options* opt, b200lp_engine** out);
 int b200lp_destroy(b200lp_engine* e);
 
 /* H2D of A (col-major m x n), b (m), c (n) (v4:269-271) followed by the slack-basis
@@ -126,6 +148,9 @@ int b200lp_run(b200lp_engine* e, int64_t iterations, b200lp_result* res);
 /* same, without waiting: returns after the launch; pair with b200lp_wait() */
 int b200lp_run_async(b200lp_engine* e, int64_t iterations);
 int b200lp_wait(b200lp_engine* e, b200lp_result* res);
+/* ask a running loop (b200lp_run_async, or b200lp_run on another thread) to stop at its next iteration boundary;
+ * state stays consistent and the run can be continued.  The kernel polls one word per iteration. */
+int b200lp_abort(b200lp_engine* e);
 
 /* D2H of the basis-ordered solution (v4:366-367); any pointer may be NULL */
 int b200lp_download(b200lp_engine* e, void* x_b, int32_t* b_ixs, void* y);
@@ -173,7 +198,8 @@ int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int
 /* ---- numerical health (the reference lists refactorisation / small-pivot guards as open, README.md:29-30) ----
  * max_i |(B^-1 b)_i - x_b_i| and max_i |x_b_i| after flushing a pending rank-1 update: how far the product-form
  * inverse and the linearly updated x_b (v4:347-348) have drifted apart.  One extra pass over B^-1; call it between
- * runs (it overwrites alpha).  Changes nothing the loop reads afterwards.  Single GPU. */
+ * runs (it overwrites alpha).  Changes nothing the loop reads afterwards.  On a sharded engine (one rank of a
+ * multi-process run) the maxima are over the rank's own rows; b200lp_create_multi engines return the global ones. */
 int b200lp_check_basis(b200lp_engine* e, double* xb_err, double* xb_scale);
 
 /* ---- in-kernel phase profile (options.profile > 0) ----

@@ -23,6 +23,7 @@ EXPORTS = [
     "b200lp_create_sharded", "b200lp_ipc_handle_bytes", "b200lp_ipc_export", "b200lp_ipc_import", "b200lp_shard_rows",
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
     "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile", "b200lp_check_basis",
+    "b200lp_solve_f64_multi", "b200lp_solve_f32_multi", "b200lp_create_multi", "b200lp_abort",
     # include/b200lp_io.h
     "b200lp_read_lp", "b200lp_write_lp_text", "b200lp_write_lp_binary", "b200lp_free_problem",
 ]
@@ -32,11 +33,12 @@ class Options(C.Structure):
     _fields_ = [("eps", C.c_double), ("max_iter", C.c_int64), ("device", C.c_int32), ("grid_ctas", C.c_int32),
                 ("tile_shape", C.c_int32), ("check_slack", C.c_int32), ("mode", C.c_int32), ("profile", C.c_int32),
                 ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32),
-                ("price_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("price_mode", C.c_int32), ("ratio_group_rows", C.c_int32), ("pivot_tol", C.c_double),
+                ("price_tail", C.c_int32), ("fuse_book2", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Result(C.Structure):
-    _fields_ = [("status", C.c_int32), ("reserved", C.c_int32), ("iterations", C.c_int64), ("pivots", C.c_int64),
+    _fields_ = [("status", C.c_int32), ("aborted", C.c_int32), ("iterations", C.c_int64), ("pivots", C.c_int64),
                 ("z", C.c_double), ("min_reduced_cost", C.c_double), ("ms_upload", C.c_double),
                 ("ms_solve", C.c_double), ("ms_download", C.c_double), ("kernel_launches", C.c_int64)]
 
@@ -70,6 +72,10 @@ def lib() -> C.CDLL:
         "b200lp_default_options": (None, [PO]),
         "b200lp_solve_f64": (C.c_int, [vp, vp, vp, i64, i64, PO, vp, vp, vp, i64, PR]),
         "b200lp_solve_f32": (C.c_int, [vp, vp, vp, i64, i64, PO, vp, vp, vp, i64, PR]),
+        "b200lp_solve_f64_multi": (C.c_int, [vp, vp, vp, i64, i64, PO, C.POINTER(i32), i32, vp, vp, vp, i64, PR]),
+        "b200lp_solve_f32_multi": (C.c_int, [vp, vp, vp, i64, i64, PO, C.POINTER(i32), i32, vp, vp, vp, i64, PR]),
+        "b200lp_create_multi": (C.c_int, [i32, i64, i64, C.POINTER(i32), i32, PO, C.POINTER(vp)]),
+        "b200lp_abort": (C.c_int, [vp]),
         "b200lp_set_memory_cache": (C.c_int, [i32]),
         "b200lp_create": (C.c_int, [i32, i64, i64, PO, C.POINTER(vp)]),
         "b200lp_destroy": (C.c_int, [vp]),

@@ -61,6 +61,7 @@ struct b200lp_engine {
 	virtual int shard_rows(int64_t* row0, int64_t* rows) = 0;
 	virtual int download_profile(uint64_t* out, int64_t cap_iters, int64_t* n_iters) = 0;
 	virtual int check_basis(double* xb_err, double* xb_scale) = 0;
+	virtual int abort() = 0;
 	cudaStream_t stream = nullptr;
 	int rank = 0, nranks = 1;
 	int grid = 0;
@@ -70,8 +71,11 @@ struct b200lp_engine {
 
 namespace {
 
+template <typename T> class MultiEngine;
+
 template <typename T>
 class Engine final : public b200lp_engine {
+	friend class MultiEngine<T>;
 public:
 	Engine(int64_t m, int64_t n, const b200lp_options& o, int rank_, int nranks_) : opt(o) {
 		std::memset(&d, 0, sizeof(d));
@@ -193,6 +197,19 @@ public:
 			if (tiles >= 96LL * grid) { wc = cand_wc; break; }
 		}
 		if (opt.tile_shape == 1 || opt.tile_shape == 2 || opt.tile_shape == 4 || opt.tile_shape == 8) wc = opt.tile_shape;
+		// row groups of the update+FTRAN pass: the ratio test of a group runs as soon as its last tile is done
+		{
+			const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
+			const long long ntr = (d.ldb + tr - 1) / tr;
+			const long long want = opt.ratio_group_rows > 0 ? opt.ratio_group_rows : 256;
+			d.rg = (int)std::max<long long>(1, want / tr);
+			d.ngrp = (int)std::max<long long>(1, (ntr + d.rg - 1) / d.rg);
+			CU(alloc(&d.rcand, (size_t)d.ngrp + 1));
+			CU(alloc(&d.rcnt, (size_t)d.ngrp + 1));
+			CU(alloc(&d.grp_done, (size_t)d.ngrp + 1));
+			CU(cudaMemsetAsync(d.grp_done, 0, ((size_t)d.ngrp + 1) * sizeof(unsigned int), stream));
+		}
+		d.pivot_tol = sizeof(T) == 4 ? (double)(float)opt.pivot_tol : opt.pivot_tol;
 		return B200LP_OK;
 	}
 
@@ -238,6 +255,15 @@ public:
 		if (col0 != d.col0 || ncols != d.nsl)
 			return fail(B200LP_ERR_ARG, "upload_columns: block is not this rank's column shard (see b200lp_shard_columns)");
 		return upload_block(Acols, bv, cv);
+	}
+
+	// multi-GPU front door inside one process: the caller holds the whole host matrix and says how many of its
+	// leading columns are data (n - m with an identity slack block, n otherwise); this rank takes its block
+	int upload_shard(const void* A_full, long long ns_new, const void* bv, const void* cv) {
+		CU(cudaSetDevice(opt.device));
+		if (int rc = settle()) return rc;
+		CU(set_columns(ns_new));
+		return upload_block(static_cast<const T*>(A_full) + (size_t)d.col0 * d.m, bv, cv);
 	}
 
 	int upload_block(const void* Av, const void* bv, const void* cv) {
@@ -288,9 +314,14 @@ public:
 		return reset();
 	}
 
+	// a launch may still be running: the host mirror of the control block (pending, xepoch, counters) is only
+	// valid after wait()
+	int settle() { return in_flight ? wait(nullptr) : B200LP_OK; }
+
 	int reset() override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "reset before upload/generate");
 		CU(cudaSetDevice(opt.device));
+		if (int rc = settle()) return rc;
 		k_reset<T><<<num_sms * 8, 256, 0, stream>>>(d);
 		launches++;
 		CU(cudaGetLastError());
@@ -303,30 +334,34 @@ public:
 
 	// ---- the loop ------------------------------------------------------
 
-	int run_async(int64_t iters) override {
+	// everything of run_async up to the launch: 1 = nothing to launch (done / no iterations), 0 = go, < 0 error
+	int prepare_run(int64_t iters) {
 		if (!have_data) return fail(B200LP_ERR_STATE, "run before upload/generate");
 		CU(cudaSetDevice(opt.device));
-		if (in_flight) {           // host mirror of the control block is stale until wait()
-			int rc = wait(nullptr);
-			if (rc) return rc;
-		}
+		if (int rc = settle()) return rc;
 		in_flight = true;
 		if (hc.done || iters <= 0) {
 			CU(cudaEventRecord(ev0, stream));
 			CU(cudaEventRecord(ev1, stream));
-			return B200LP_OK;
+			return 1;
 		}
-		if (opt.mode == 1 && nranks == 1) return run_phases(iters);
-		if (tiny_ok()) return run_tiny(iters);
+		if (opt.mode == 1 && nranks == 1) { int rc = run_phases(iters); return rc ? rc : 1; }
+		if (tiny_ok()) { int rc = run_tiny(iters); return rc ? rc : 1; }
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
 		if (d.prof_cap > 0) CU(cudaMemsetAsync(d.prof, 0, (size_t)d.prof_cap * NSTAMP * sizeof(unsigned long long), stream));
 		prof_iter0 = hc.iter;
 		CU(cudaEventRecord(ev0, stream));
+		return 0;
+	}
+
+	int run_async(int64_t iters) override {
+		const int pr = prepare_run(iters);
+		if (pr != 0) return pr < 0 ? pr : B200LP_OK;
 		void* args[] = {&d};
 		const void* fn;
 		if (nranks > 1) {
-			if (!peers_mapped) return fail(B200LP_ERR_STATE, "sharded engine: ipc_import has not been called");
+			if (!peers_mapped) return fail(B200LP_ERR_STATE, "sharded engine: peers are not mapped (ipc_import / create_multi)");
 			fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1>
 			   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2>
 			   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4>
@@ -343,20 +378,37 @@ public:
 		return B200LP_OK;
 	}
 
+	// ask the running loop to stop at its next iteration boundary: one word written by a copy on a second stream
+	int abort() override {
+		CU(cudaSetDevice(opt.device));
+		if (!in_flight) return B200LP_OK;
+		if (!abort_stream) CU(cudaStreamCreateWithFlags(&abort_stream, cudaStreamNonBlocking));
+		int* one = reinterpret_cast<int*>(static_cast<unsigned char*>(pinned) + sizeof(Ctl));
+		*one = 1;
+		CU(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(d.ctl) + offsetof(Ctl, abort_req), one, sizeof(int),
+			cudaMemcpyHostToDevice, abort_stream));
+		CU(cudaStreamSynchronize(abort_stream));
+		return B200LP_OK;
+	}
+
 	int wait(b200lp_result* res) override {
 		CU(cudaSetDevice(opt.device));
 		CU(cudaStreamSynchronize(stream));
 		CU(cudaGetLastError());
 		float ms = 0;
+		bool was_aborted = false;
 		if (in_flight) {
 			CU(cudaEventElapsedTime(&ms, ev0, ev1));
 			CU(pull_ctl());
+			was_aborted = hc.aborted != 0;
+			hc.abort_req = hc.abort_latched = hc.aborted = 0;
 		}
 		in_flight = false;
 		if (hc.bad) return fail(B200LP_ERR_CUDA, "sharded engine: a peer GPU did not answer within 20 s (the engine must be destroyed)");
 		if (res) {
 			std::memset(res, 0, sizeof(*res));
 			res->status = hc.status;
+			res->aborted = was_aborted ? 1 : 0;
 			res->iterations = hc.iter;
 			res->pivots = hc.pivots;
 			res->z = hc.z;
@@ -381,6 +433,7 @@ public:
 
 	int download_binv(void* Binv) override {
 		CU(cudaSetDevice(opt.device));
+		if (int rc = settle()) return rc;
 		CU(cudaStreamSynchronize(stream));
 		if (hc.pending) {
 			launch_update_ftran(true, false, 0);
@@ -396,12 +449,12 @@ public:
 		return B200LP_OK;
 	}
 
-	// numerical health of the product-form inverse: max_i |(B^-1 b)_i - x_b_i|.  One extra pass over B^-1, between runs.
+	// numerical health of the product-form inverse: max_i |(B^-1 b)_i - x_b_i| over the rows this engine owns
+	// (all of them on one GPU).  One extra pass over the local block of B^-1, between runs.
 	int check_basis(double* xb_err, double* xb_scale) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "check_basis before upload/generate");
-		if (nranks > 1) return fail(B200LP_ERR_STATE, "check_basis is single-GPU only");
 		CU(cudaSetDevice(opt.device));
-		if (in_flight) { int rc = wait(nullptr); if (rc) return rc; }
+		if (int rc = settle()) return rc;
 		if (hc.pending) {
 			launch_update_ftran(true, false, 0);
 			CU(cudaGetLastError());
@@ -416,15 +469,18 @@ public:
 		else if (wc == 2) k_ftran_vec<T, 2><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
 		else if (wc == 4) k_ftran_vec<T, 4><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
 		else k_ftran_vec<T, 8><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
-		k_ratio<T><<<grid, NT, 0, stream>>>(d);          // sums the chunk partials into alpha (the candidates are ignored)
+		k_sum_partials<T><<<num_sms, NT, 0, stream>>>(d, d.acol);     // (B^-1 b) of the local rows -> scratch
 		launches += 2;
 		CU(cudaGetLastError());
-		std::vector<T> a((size_t)d.m), x((size_t)d.m);
-		CU(cudaMemcpyAsync(a.data(), d.alpha, d.m * sizeof(T), cudaMemcpyDeviceToHost, stream));
-		CU(cudaMemcpyAsync(x.data(), d.x_b, d.m * sizeof(T), cudaMemcpyDeviceToHost, stream));
+		const long long rows = std::max<long long>(0, std::min<long long>(d.m, d.row0 + d.ldb) - d.row0);
+		std::vector<T> a((size_t)std::max<long long>(rows, 1)), x((size_t)std::max<long long>(rows, 1));
+		if (rows > 0) {
+			CU(cudaMemcpyAsync(a.data(), d.acol, rows * sizeof(T), cudaMemcpyDeviceToHost, stream));
+			CU(cudaMemcpyAsync(x.data(), d.x_b + d.row0, rows * sizeof(T), cudaMemcpyDeviceToHost, stream));
+		}
 		CU(cudaStreamSynchronize(stream));
 		double err = 0, scale = 0;
-		for (long long i = 0; i < d.m; ++i) {
+		for (long long i = 0; i < rows; ++i) {
 			err = std::max(err, std::fabs((double)a[i] - (double)x[i]));
 			scale = std::max(scale, std::fabs((double)x[i]));
 		}
@@ -457,6 +513,7 @@ public:
 	int phase_price(int64_t* p, double* min_e) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
 		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
+		if (in_flight && !phase_loop) { if (int rc = settle()) return rc; }
 		CU(cudaSetDevice(opt.device));
 		CU(zero_tickets());
 		k_price<T><<<grid, NT, DYN_SMEM_BYTES, stream>>>(d);
@@ -472,6 +529,7 @@ public:
 	int phase_update_ftran(int64_t p) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
 		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
+		if (in_flight && !phase_loop) { if (int rc = settle()) return rc; }
 		if (p < 0 || p >= d.n) return fail(B200LP_ERR_ARG, "entering column out of range");
 		CU(cudaSetDevice(opt.device));
 		launch_update_ftran(hc.pending != 0, true, p);
@@ -485,6 +543,7 @@ public:
 	int phase_ratio(int64_t* q, int64_t* eligible) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
 		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
+		if (in_flight && !phase_loop) { if (int rc = settle()) return rc; }
 		CU(cudaSetDevice(opt.device));
 		k_ratio<T><<<grid, NT, 0, stream>>>(d);
 		k_pick<T><<<1, NT, 0, stream>>>(d, grid, 1);
@@ -501,6 +560,7 @@ public:
 	int phase_pivot_update(int64_t p, int64_t q) override {
 		if (!have_data) return fail(B200LP_ERR_STATE, "phase before upload/generate");
 		if (nranks > 1) return fail(B200LP_ERR_STATE, "phase entry points are single-GPU only");
+		if (in_flight && !phase_loop) { if (int rc = settle()) return rc; }
 		if (p < 0 || p >= d.n || q < 0 || q >= d.m) return fail(B200LP_ERR_ARG, "pivot out of range");
 		CU(cudaSetDevice(opt.device));
 		k_book1<T><<<grid, NT, 0, stream>>>(d, p, q);
@@ -604,6 +664,14 @@ private:
 		// TMA ring at 1 GB (8-GPU shard of m = 32768) and 8 GB; the ring is kept for the largest shards.
 		d.price_direct = opt.price_mode == 1 ? 0 : opt.price_mode == 2 ? 1
 		               : ((size_t)d.ld * (size_t)nsl_new * sizeof(T) <= ((size_t)2 << 30) ? 1 : 0);
+		// x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass: y must fit in the (idle) ring memory
+		// and pricing must read y from there (register-staged path); single GPU only
+		d.fuse_book2 = (opt.fuse_book2 >= 0 && nranks == 1 && d.price_direct && opt.mode == 0 &&
+		                (size_t)d.ld * sizeof(T) <= (size_t)DYN_SMEM_BYTES) ? 1 : 0;
+		// single-column work items at the end of the pricing pass: only where one column alone keeps 16 loads per
+		// thread in flight (ld >= 16 row steps of the CTA), two per CTA
+		d.price_tail = opt.price_tail < 0 ? 0 : opt.price_tail > 0 ? opt.price_tail
+		             : (d.ld >= 16LL * NT * VecT<T>::N ? 2 * grid : 0);
 		// unit (slack) columns priced without matrix bytes: none when the slack block was not recognised
 		const long long nunit = d.n - ns_new;
 		d.k0 = nunit * rank / nranks;
@@ -620,6 +688,7 @@ private:
 	}
 
 	void release() {
+		cudaSetDevice(opt.device);
 		if (stream) cudaStreamSynchronize(stream);
 		if (l2_persist_bytes) cudaCtxResetPersistingL2Cache();
 		for (void* p : opened) cudaIpcCloseMemHandle(p);
@@ -631,6 +700,7 @@ private:
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
 		if (stream) cudaStreamDestroy(stream);
+		if (abort_stream) cudaStreamDestroy(abort_stream);
 	}
 
 	// Is S (m x m, column-major, host) the identity?  A streaming OR over the raw bits of every column (sign bit
@@ -734,6 +804,7 @@ private:
 	// mode 1: the loop of v4:286-359 driven from the host, one launch per phase and
 	// one blocking read-back per decision (what the reference does, minus the libraries)
 	int run_phases(int64_t iters) {
+		struct Guard { bool& f; Guard(bool& g) : f(g) { f = true; } ~Guard() { f = false; } } guard(phase_loop);
 		CU(cudaEventRecord(ev0, stream));
 		const long long it_end = hc.iter + iters;
 		hc.status = B200LP_STATUS_MAX_ITER;
@@ -772,10 +843,236 @@ private:
 	bool peers_mapped = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	int num_sms = 0, max_grid = 0, wc = 1;
-	bool have_data = false, in_flight = false;
+	bool have_data = false, in_flight = false, phase_loop = false;
+	cudaStream_t abort_stream = nullptr;
 	int64_t launches = 0;
 	long long prof_iter0 = 0;
 	size_t l2_persist_bytes = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Several GPUs behind ONE handle (b200lp_create_multi / b200lp_solve_*_multi): one rank of the sharded engine per
+// listed device, all in this process.  Peers are mapped with cudaDeviceEnablePeerAccess and plain pointers (the
+// multi-process front end exchanges CUDA IPC handles instead); launches, copies and waits fan out from the
+// calling host thread, uploads run on one host thread per rank so that every GPU's PCIe link is busy.
+// A device listed more than once hosts several ranks: they must share ONE cooperative launch
+// (simplex_persistent_sharded_emu), because kernels that spin on each other may never be separate launches on one GPU.
+template <typename T>
+class MultiEngine final : public b200lp_engine {
+public:
+	MultiEngine(int64_t m, int64_t n) : m_(m), n_(n) {}
+	~MultiEngine() override {
+		for (auto* e : eng) delete e;
+		if (devs_d) { cudaSetDevice(devices[0]); cudaFree(devs_d); }
+		if (done_ev) cudaEventDestroy(done_ev);
+	}
+
+	int init(const b200lp_options& o, const int32_t* devs, int ndev) {
+		R = ndev;
+		devices.assign(devs, devs + ndev);
+		int same = 0;
+		for (int r = 0; r < R; ++r) same += devices[r] == devices[0];
+		emu = R > 1 && same == R;
+		if (!emu)
+			for (int r = 0; r < R; ++r)
+				for (int q = 0; q < r; ++q)
+					if (devices[q] == devices[r])
+						return fail(B200LP_ERR_ARG, "devices: either all distinct, or one device repeated for every rank");
+		for (int r = 0; r < R; ++r) {
+			b200lp_options orr = o;
+			orr.device = devices[r];
+			if (emu && orr.tile_shape == 0) orr.tile_shape = 8;   // one kernel instance serves all ranks
+			auto* e = new Engine<T>(m_, n_, orr, r, R);
+			eng.push_back(e);
+			if (int rc = e->init()) return rc;
+		}
+		if (emu) {
+			CU(cudaSetDevice(devices[0]));
+			int occ = 0;
+			CU(cudaFuncSetAttribute(emu_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_BYTES));
+			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, emu_fn(), NT, DYN_SMEM_BYTES));
+			if (occ < 1) return fail(B200LP_ERR_CUDA, "emulated multi-rank kernel does not fit on an SM");
+			int gr = std::max(1, std::min(eng[0]->grid, occ * eng[0]->num_sms / R));
+			for (auto* e : eng) e->grid = gr;
+			CU(cudaMalloc((void**)&devs_d, sizeof(Dev<T>) * R));
+			CU(cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming));
+		} else {
+			for (int r = 0; r < R; ++r) {
+				CU(cudaSetDevice(devices[r]));
+				for (int q = 0; q < R; ++q) {
+					if (q == r) continue;
+					int can = 0;
+					CU(cudaDeviceCanAccessPeer(&can, devices[r], devices[q]));
+					if (!can) return fail(B200LP_ERR_CUDA, "devices cannot access each other's memory (no NVLink / P2P)");
+					cudaError_t e_ = cudaDeviceEnablePeerAccess(devices[q], 0);
+					if (e_ == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+					else if (e_ != cudaSuccess) return fail(B200LP_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e_));
+				}
+			}
+		}
+		stream = eng[0]->stream;
+		grid = eng[0]->grid;
+		return B200LP_OK;
+	}
+
+	// ---- data in
+	int upload(const void* A, const void* b, const void* c) override {
+		// the identity check of the slack block (m*m host reads) runs beside the copies of the structural columns
+		bool ident = true;
+		std::thread chk([&] { ident = !eng[0]->opt.check_slack || Engine<T>::host_is_identity(static_cast<const T*>(A) + (size_t)(n_ - m_) * m_, m_); });
+		int rc = upload_all(A, n_ - m_, b, c);
+		chk.join();
+		if (rc) return rc;
+		if (!ident && (rc = upload_all(A, n_, b, c))) return rc;   // rare: the block is data, all n columns are stored
+		return connect();
+	}
+	int upload_unchecked(const void* A, const void* b, const void* c) override { return upload(A, b, c); }
+	bool slack_is_identity(const void*) const override { return true; }
+	int upload_columns(const void*, int64_t, int64_t, const void*, const void*) override { return only_single("upload_columns"); }
+	int shard_columns(int64_t* col0, int64_t* ncols) override { if (col0) *col0 = 0; if (ncols) *ncols = n_ - m_; return B200LP_OK; }
+	int shard_rows(int64_t* row0, int64_t* rows) override { if (row0) *row0 = 0; if (rows) *rows = m_; return B200LP_OK; }
+	int generate_dense(uint64_t seed) override {
+		for (auto* e : eng) if (int rc = e->generate_dense(seed)) return rc;
+		return connect();
+	}
+	int reset() override {
+		for (auto* e : eng) if (int rc = e->reset()) return rc;
+		return B200LP_OK;
+	}
+
+	// ---- the loop
+	int run_async(int64_t iters) override {
+		if (!connected) return fail(B200LP_ERR_STATE, "run before upload/generate");
+		if (!emu) {
+			for (auto* e : eng) if (int rc = e->run_async(iters)) return rc;
+			return B200LP_OK;
+		}
+		int go = 0;
+		for (auto* e : eng) {
+			const int pr = e->prepare_run(iters);
+			if (pr < 0) return pr;
+			go += pr == 0;
+		}
+		if (go == 0) return B200LP_OK;
+		if (go != R) return fail(B200LP_ERR_STATE, "ranks disagree on whether there is work left");
+		CU(cudaSetDevice(devices[0]));
+		std::vector<Dev<T>> h;
+		for (auto* e : eng) h.push_back(e->d);
+		for (int r = 1; r < R; ++r) CU(cudaStreamSynchronize(eng[r]->stream));
+		CU(cudaMemcpyAsync(devs_d, h.data(), sizeof(Dev<T>) * R, cudaMemcpyHostToDevice, stream));
+		CU(cudaStreamSynchronize(stream));              // h goes out of scope
+		CU(cudaEventRecord(eng[0]->ev0, stream));
+		int Rarg = R;
+		void* args[] = {&devs_d, &Rarg};
+		CU(cudaLaunchCooperativeKernel(emu_fn(), dim3(eng[0]->grid * R), dim3(NT), args, DYN_SMEM_BYTES, stream));
+		eng[0]->launches++;
+		CU(cudaEventRecord(eng[0]->ev1, stream));
+		CU(cudaEventRecord(done_ev, stream));
+		for (int r = 1; r < R; ++r) {                    // the other ranks' streams wait for the shared launch
+			CU(cudaStreamWaitEvent(eng[r]->stream, done_ev, 0));
+			CU(cudaEventRecord(eng[r]->ev1, eng[r]->stream));
+		}
+		return B200LP_OK;
+	}
+	int wait(b200lp_result* res) override {
+		b200lp_result first;
+		std::memset(&first, 0, sizeof(first));
+		double ms = 0;
+		int rc_all = B200LP_OK;
+		for (int r = 0; r < R; ++r) {
+			b200lp_result rr;
+			const int rc = eng[r]->wait(&rr);
+			if (rc && !rc_all) rc_all = rc;
+			if (r == 0) first = rr;
+			ms = std::max(ms, rr.ms_solve);
+		}
+		first.ms_solve = ms;
+		int64_t l = 0;
+		for (auto* e : eng) l += e->launches;
+		first.kernel_launches = l;
+		if (res) *res = first;
+		return rc_all;
+	}
+	int abort() override {
+		for (auto* e : eng) if (int rc = e->abort()) return rc;
+		return B200LP_OK;
+	}
+
+	// ---- data out (every O(m) vector is replicated: rank 0 answers)
+	int download(void* x_b, int32_t* b_ixs, void* y) override { if (int rc = settle_all()) return rc; return eng[0]->download(x_b, b_ixs, y); }
+	int download_trace(int32_t* pq, int64_t cap, int64_t* n_out) override { if (int rc = settle_all()) return rc; return eng[0]->download_trace(pq, cap, n_out); }
+	int download_vector(int32_t which, void* out) override { if (int rc = settle_all()) return rc; return eng[0]->download_vector(which, out); }
+	int download_profile(uint64_t* out, int64_t cap, int64_t* n) override { return eng[0]->download_profile(out, cap, n); }
+	int download_binv(void* Binv) override {
+		T* out = static_cast<T*>(Binv);
+		for (auto* e : eng) {
+			int64_t r0 = 0, rows = 0;
+			e->shard_rows(&r0, &rows);
+			if (rows <= 0) continue;
+			std::vector<T> blk((size_t)rows * m_);
+			if (int rc = e->download_binv(blk.data())) return rc;
+			for (int64_t j = 0; j < m_; ++j)
+				std::memcpy(out + (size_t)j * m_ + r0, blk.data() + (size_t)j * rows, (size_t)rows * sizeof(T));
+		}
+		return B200LP_OK;
+	}
+	int check_basis(double* xb_err, double* xb_scale) override {
+		double err = 0, scale = 0;
+		for (auto* e : eng) {
+			double a = 0, b = 0;
+			if (int rc = e->check_basis(&a, &b)) return rc;
+			err = std::max(err, a);
+			scale = std::max(scale, b);
+		}
+		if (xb_err) *xb_err = err;
+		if (xb_scale) *xb_scale = scale;
+		return B200LP_OK;
+	}
+	int phase_price(int64_t*, double*) override { return only_single("phase_price"); }
+	int phase_update_ftran(int64_t) override { return only_single("phase_update_ftran"); }
+	int phase_ratio(int64_t*, int64_t*) override { return only_single("phase_ratio"); }
+	int phase_pivot_update(int64_t, int64_t) override { return only_single("phase_pivot_update"); }
+	int ipc_export(void*) override { return only_single("ipc_export"); }
+	int ipc_import(const void*, int) override { return only_single("ipc_import"); }
+	int64_t bytes_per_pivot() const override { return eng[0]->bytes_per_pivot(); }
+
+private:
+	static int only_single(const char* what) { return fail(B200LP_ERR_STATE, std::string(what) + " is not available on a multi-GPU handle"); }
+	int settle_all() { for (auto* e : eng) if (int rc = e->settle()) return rc; return B200LP_OK; }
+
+	const void* emu_fn() const { return (const void*)simplex_persistent_sharded_emu<T, 8>; }
+
+	int upload_all(const void* A, long long ns_new, const void* b, const void* c) {
+		std::vector<int> rcs(R, 0);
+		std::vector<std::string> errs(R);
+		std::vector<std::thread> th;
+		for (int r = 0; r < R; ++r)
+			th.emplace_back([&, r] { rcs[r] = eng[r]->upload_shard(A, ns_new, b, c); if (rcs[r]) errs[r] = g_err; });
+		for (auto& t : th) t.join();
+		for (int r = 0; r < R; ++r) if (rcs[r]) return fail(rcs[r], errs[r]);
+		ns = ns_new;
+		return B200LP_OK;
+	}
+
+	// every rank learns every rank's A shard and mailbox (same address space: plain pointers)
+	int connect() {
+		for (auto* e : eng) {
+			for (int q = 0; q < R; ++q) { e->d.A_peer[q] = eng[q]->hA; e->d.mbox_peer[q] = eng[q]->mbox; }
+			e->peers_mapped = true;
+		}
+		connected = true;
+		ms_upload = 0;
+		for (auto* e : eng) ms_upload = std::max(ms_upload, e->ms_upload);
+		return B200LP_OK;
+	}
+
+	int64_t m_, n_;
+	int R = 0;
+	bool emu = false, connected = false;
+	std::vector<int> devices;
+	std::vector<Engine<T>*> eng;
+	Dev<T>* devs_d = nullptr;
+	cudaEvent_t done_ev = nullptr;
 };
 
 template <typename T>
@@ -798,6 +1095,58 @@ int create_engine(int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine
 	if (rc) { delete e; return rc; }
 	*out = e;
 	return B200LP_OK;
+}
+
+template <typename T>
+int create_multi(int64_t m, int64_t n, const b200lp_options* opt, const int32_t* devices, int ndev, b200lp_engine** out) {
+	if (!out) return fail(B200LP_ERR_ARG, "out is NULL");
+	*out = nullptr;
+	if (!devices || ndev < 1 || ndev > MAXR) return fail(B200LP_ERR_ARG, "need 1 <= ndev <= 8 device ordinals");
+	b200lp_options o;
+	if (opt) o = *opt; else b200lp_default_options(&o);
+	if (ndev == 1) {
+		o.device = devices[0];
+		return create_engine<T>(m, n, &o, out);
+	}
+	if (m <= 0 || n <= 0 || m > n) return fail(B200LP_ERR_ARG, "need 0 < m <= n (v4:402)");
+	if (n >= ((int64_t)1 << 31)) return fail(B200LP_ERR_ARG, "n must fit a 32-bit basis index");
+	int have = 0;
+	if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) {
+		cudaGetLastError();
+		return fail(B200LP_ERR_NO_GPU, "no CUDA device: the engine has no CPU fallback");
+	}
+	for (int r = 0; r < ndev; ++r)
+		if (devices[r] < 0 || devices[r] >= have) return fail(B200LP_ERR_ARG, "device ordinal out of range");
+	auto* e = new MultiEngine<T>(m, n);
+	int rc = e->init(o, devices, ndev);
+	if (rc) { delete e; return rc; }
+	*out = e;
+	return B200LP_OK;
+}
+
+// the one-call solve over several GPUs: create, upload (slack check beside the copies), run, read back, destroy
+template <typename T>
+int solve_multi(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b200lp_options* opt,
+		const int32_t* devices, int ndev, T* x_b, int32_t* b_ixs, int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	if (!A || !b || !c) return fail(B200LP_ERR_ARG, "A, b, c must not be NULL");
+	b200lp_options o;
+	if (opt) o = *opt; else b200lp_default_options(&o);
+	b200lp_engine* e = nullptr;
+	int rc = create_multi<T>(m, n, &o, devices, ndev, &e);
+	if (rc) return rc;
+	b200lp_result r;
+	std::memset(&r, 0, sizeof(r));
+	do {
+		if ((rc = e->upload(A, b, c))) break;
+		if ((rc = e->run_async(o.max_iter))) break;
+		if ((rc = e->wait(&r))) break;
+		r.ms_upload = e->ms_upload;
+		if ((rc = e->download(x_b, b_ixs, nullptr))) break;
+		if (trace_pq && trace_cap > 0 && (rc = e->download_trace(trace_pq, trace_cap, nullptr))) break;
+	} while (0);
+	if (res) *res = r;
+	delete e;
+	return rc;
 }
 
 // One engine kept between calls of b200lp_solve_* (b200lp_set_memory_cache): creating and destroying 16 GB of
@@ -850,6 +1199,7 @@ int solve_once(const T* A, const T* b, const T* c, int64_t m, int64_t n, const b
 			t = Clk::now();
 			if ((rc = e->run_async(o.max_iter))) break;
 			if (!e->slack_is_identity(A)) {           // rare: the block is data -> store and price all n columns
+				if ((rc = e->abort())) break;            // the optimistic run stops at its next iteration boundary
 				if ((rc = e->wait(nullptr))) break;
 				if ((rc = e->upload(A, b, c))) break;
 				if ((rc = e->run_async(o.max_iter))) break;
@@ -958,6 +1308,39 @@ int b200lp_solve_f32(const float* A, const float* b, const float* c, int64_t m, 
 	return solve_once<float>(A, b, c, m, n, opt, x_b, b_ixs, trace_pq, trace_cap, res);
 }
 
+int b200lp_solve_f64_multi(const double* A, const double* b, const double* c, int64_t m, int64_t n,
+		const b200lp_options* opt, const int32_t* devices, int32_t ndev, double* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	if (!devices || ndev < 1 || ndev > MAXR) return fail(B200LP_ERR_ARG, "need 1 <= ndev <= 8 device ordinals");
+	if (ndev == 1) {
+		b200lp_options o;
+		if (opt) o = *opt; else b200lp_default_options(&o);
+		o.device = devices[0];
+		return solve_once<double>(A, b, c, m, n, &o, x_b, b_ixs, trace_pq, trace_cap, res);
+	}
+	return solve_multi<double>(A, b, c, m, n, opt, devices, ndev, x_b, b_ixs, trace_pq, trace_cap, res);
+}
+
+int b200lp_solve_f32_multi(const float* A, const float* b, const float* c, int64_t m, int64_t n,
+		const b200lp_options* opt, const int32_t* devices, int32_t ndev, float* x_b, int32_t* b_ixs,
+		int32_t* trace_pq, int64_t trace_cap, b200lp_result* res) {
+	if (!devices || ndev < 1 || ndev > MAXR) return fail(B200LP_ERR_ARG, "need 1 <= ndev <= 8 device ordinals");
+	if (ndev == 1) {
+		b200lp_options o;
+		if (opt) o = *opt; else b200lp_default_options(&o);
+		o.device = devices[0];
+		return solve_once<float>(A, b, c, m, n, &o, x_b, b_ixs, trace_pq, trace_cap, res);
+	}
+	return solve_multi<float>(A, b, c, m, n, opt, devices, ndev, x_b, b_ixs, trace_pq, trace_cap, res);
+}
+
+int b200lp_create_multi(int32_t dtype, int64_t m, int64_t n, const int32_t* devices, int32_t ndev,
+		const b200lp_options* opt, b200lp_engine** out) {
+	if (dtype == B200LP_F64) return create_multi<double>(m, n, opt, devices, ndev, out);
+	if (dtype == B200LP_F32) return create_multi<float>(m, n, opt, devices, ndev, out);
+	return fail(B200LP_ERR_ARG, "dtype must be B200LP_F32 or B200LP_F64");
+}
+
 int b200lp_create(int32_t dtype, int64_t m, int64_t n, const b200lp_options* opt, b200lp_engine** out) {
 	if (dtype == B200LP_F64) return create_engine<double>(m, n, opt, out);
 	if (dtype == B200LP_F32) return create_engine<float>(m, n, opt, out);
@@ -1017,6 +1400,7 @@ int b200lp_run(b200lp_engine* e, int64_t iterations, b200lp_result* res) {
 }
 int b200lp_run_async(b200lp_engine* e, int64_t iterations) { NEED(e); return e->run_async(iterations); }
 int b200lp_wait(b200lp_engine* e, b200lp_result* res) { NEED(e); return e->wait(res); }
+int b200lp_abort(b200lp_engine* e) { NEED(e); return e->abort(); }
 int b200lp_download(b200lp_engine* e, void* x_b, int32_t* b_ixs, void* y) { NEED(e); return e->download(x_b, b_ixs, y); }
 int b200lp_download_binv(b200lp_engine* e, void* Binv) { NEED(e); if (!Binv) return fail(B200LP_ERR_ARG, "Binv is NULL"); return e->download_binv(Binv); }
 int b200lp_download_trace(b200lp_engine* e, int32_t* pq, int64_t cap, int64_t* n_out) { NEED(e); return e->download_trace(pq, cap, n_out); }
@@ -1031,6 +1415,6 @@ int b200lp_grid_ctas(b200lp_engine* e) { return e ? e->grid : 0; }
 int b200lp_dense_columns(b200lp_engine* e) { return e ? (int)e->ns : 0; }
 int64_t b200lp_bytes_per_pivot(b200lp_engine* e) { return e ? e->bytes_per_pivot() : 0; }
 const char* b200lp_last_error(void) { return g_err.c_str(); }
-const char* b200lp_version(void) { return "b200lp 0.1 (sm_100a)"; }
+const char* b200lp_version(void) { return "b200lp 0.2 (sm_100a)"; }
 
 } // extern "C"

@@ -1,17 +1,21 @@
 // Device code of the B200 dense revised-simplex engine (sm_100a).
 //
-// One pivot of the reference loop (src/v4_cub_reduction.cu:286-359) is five
+// One pivot of the reference loop (src/v4_cub_reduction.cu:286-359) is three
 // phases separated by grid-wide barriers; all of them live in ONE persistent
 // cooperative kernel (simplex_persistent), so there is no host round trip per
 // pivot.  The same phase functions are also wrapped as stand-alone kernels for
-// unit tests and for the sharded multi-GPU driver.
+// unit tests and for the one-launch-per-phase mode.
 //
 //   price          e_j = y.A_j - c_j fused with the argmin           (v4:289-296)
+//                  its prologue applies the O(m) updates of the PREVIOUS pivot
+//                  (x_b, y, c_b, b_ixs: v4:339-356) when y fits in shared memory
 //   update_ftran   B^-1 += E_q (x) row_q  AND  alpha = B^-1_new a_p  (v4:333 + v4:307-308)
-//                  -> B^-1 crosses HBM once per pivot (read + write)
-//   ratio          alpha = sum of chunk partials, masked argmin      (v4:311-325)
+//                  -> B^-1 crosses HBM once per pivot (read + write);
+//                  the CTA that completes the last tile of a row group sums the group's
+//                  chunk partials and runs the ratio test on those rows (v4:311-325)
+//                  while the other CTAs keep streaming
 //   book1          row_q gather, E_q, the two O(m) dot products      (v4:331-332, 347, 354)
-//   book2          x_b, y, c_b, b_ixs                                (v4:339-356)
+//   (book2         x_b, y, c_b, b_ixs as a phase of its own: large m, window end)
 //
 // Layout: everything column-major like the reference (v4:59-60).  The leading
 // dimension ld is m rounded up to one warp-wide 16-byte vector row (64 doubles
@@ -80,6 +84,10 @@ struct Ctl {
 	unsigned int price_ctr;   // dynamic work tickets of the pricing phase (column groups)
 	unsigned int upd_ctr;     // dynamic work tickets of the update+FTRAN phase (tiles)
 	unsigned long long xepoch; // cross-GPU barrier epoch, monotonic over the engine's life
+	int abort_req;            // host: stop at the next iteration boundary (b200lp_abort); written while the kernel runs
+	int abort_latched;        // CTA 0's copy of abort_req, taken before it arrives at the pricing barrier
+	int aborted;              // the last launch ended because of abort_req
+	int pad0;
 	long long p, q;           // last entering column / leaving row
 	double min_e;             // last pricing minimum
 	double c_b_q;             // c_b[q] before the swap (v4:339)
@@ -100,6 +108,14 @@ struct Dev {
 	int* b_ixs;               // m
 	Cand* cand;               // one per CTA
 	long long* cnt;           // eligible rows, one per CTA
+	Cand* rcand;              // ratio-test candidate of every row group of the update+FTRAN pass
+	long long* rcnt;          // eligible rows of every row group
+	unsigned int* grp_done;   // tiles finished per row group (reset by the finisher)
+	int rg;                   // row tiles per row group
+	int ngrp;                 // row groups of the local row block
+	int fuse_book2;           // 1: the O(m) updates of a pivot ride in the prologue of the next pricing pass (y in shared memory)
+	int price_tail;           // columns at the end of the local block priced one at a time (shorter tail of the pass)
+	double pivot_tol;         // ratio-test eligibility alpha > pivot_tol (0 = the reference's strict test, v4:203)
 	Ctl* ctl;
 	int2* trace;
 	long long trace_cap;
@@ -319,11 +335,11 @@ __device__ __forceinline__ void block_argmin(double& v, long long& i, Smem& sh) 
 constexpr int NSTAMP = 16;
 // interval j runs from stamp j to stamp j+1 (the last one to stamp 0 of the next iteration)
 #define PROFILE_NAMES_JSON \
-	"{\"single\": [\"price\", \"barrier + argmin p\", \"update + FTRAN\", \"barrier\", \"ratio\", " \
-	"\"barrier + argmin q\", \"book1 (row_q, E_q, dots)\", \"barrier\", \"book2 (x_b, y)\", \"barrier\"], " \
-	"\"sharded\": [\"price\", \"X1: arrive, publish candidate, gather\", \"fetch a_p + barrier\", \"update + FTRAN\", " \
-	"\"barrier\", \"X2: alpha + ratio of local rows, publish, gather\", \"book1 (E_q, dots; owner: row_q push)\", " \
-	"\"barrier + X3 flag\", \"book2 (x_b, y)\", \"barrier\"]}"
+	"{\"single\": [\"price (+ book2 prologue)\", \"barrier + argmin p\", \"update + FTRAN + ratio groups\", \"barrier\", " \
+	"\"argmin q\", \"book1 (row_q, E_q, dots)\", \"barrier\", \"book2 (x_b, y) [unfused only]\", \"barrier [unfused only]\", \"loop\"], " \
+	"\"sharded\": [\"price\", \"X1: arrive, publish candidate, gather\", \"fetch a_p + barrier\", " \
+	"\"update + FTRAN + ratio groups (alpha slices pushed)\", \"X2: arrive, publish, gather\", " \
+	"\"book1 (E_q, dots; owner: row_q push)\", \"barrier + X3 flag\", \"book2 (x_b, y)\", \"barrier\", \"loop\"]}"
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
 	unsigned long long t;
@@ -333,8 +349,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // CTA 0 / thread 0 stamps the time at which it passes point k of iteration `itl` of this launch
 template <typename T>
-__device__ __forceinline__ void stamp(const Dev<T>& d, long long itl, int k) {
-	if (d.prof_cap > 0 && blockIdx.x == 0 && threadIdx.x == 0 && itl < d.prof_cap)
+__device__ __forceinline__ void stamp(const Dev<T>& d, long long itl, int k, int me = 0) {
+	if (d.prof_cap > 0 && me == 0 && threadIdx.x == 0 && itl < d.prof_cap)
 		d.prof[itl * NSTAMP + k] = globaltimer_ns();
 }
 
@@ -344,9 +360,9 @@ __device__ __forceinline__ void stamp(const Dev<T>& d, long long itl, int k) {
 // a release reduction (fire and forget: nobody waits for the old value) and an acquire-load spin, so the
 // arrival costs one fence and the wake-up one L2 round trip.  The acquire also invalidates L1, so plain loads
 // after the barrier see fresh data.
-__device__ __forceinline__ void grid_barrier(Ctl* ctl, unsigned long long& epoch) {
-	epoch += gridDim.x;
-	if (gridDim.x == 1) { __syncthreads(); return; }
+__device__ __forceinline__ void grid_barrier(Ctl* ctl, unsigned long long& epoch, int G) {
+	epoch += G;
+	if (G == 1) { __syncthreads(); return; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(&ctl->bar) : "memory");
@@ -531,59 +547,73 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 // third of it; measured, this path also wins by ~6 % of the pass at m = 8192 and ties with the ring above that, so
 // the host selects it up to a 2 GB A shard (Engine::set_columns).  Register-staged 16-byte loads, 16 in flight per thread; the per-column summation order is
 // the one of price_phase (thread t owns vectors t, t+256, ...), so both give the same bits.
-template <typename T>
-__device__ void price_phase_direct(const Dev<T>& d, Smem& sh, int part, int nparts) {
+//
+// Work items are handed out by the ticket counter (first item = CTA index), like the tiles of the update pass:
+// fast and slow SMs even out, results do not depend on who prices a column.  Items are groups of PRICE_NC columns
+// except for the last d.price_tail columns of the block, which go one at a time: the pass ends when the slowest CTA
+// finishes its last item, and a single column is a quarter of a group (measured on 8 GPUs, m = 32768: a group is
+// ~40 us of a ~170 us pass).
+
+// dot products of NC consecutive columns with y: per-thread partial sums reduced to one value per warp in
+// sh.wsum[buf][k][warp].  UR row steps are unrolled so that NC * UR 16-byte loads are in flight per thread.
+template <typename T, int NC, int UR>
+__device__ __forceinline__ void price_columns(const Dev<T>& d, Smem& sh, const T* ysm, long long col, int buf) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const long long ld = d.ld;
+	const T* ap[NC];
+#pragma unroll
+	for (int k = 0; k < NC; ++k) ap[k] = d.A + (col + k) * ld;
+	const T* yp = ysm ? ysm : d.y;
+	T acc[NC][VN];
+#pragma unroll
+	for (int k = 0; k < NC; ++k)
+#pragma unroll
+		for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
+#pragma unroll UR
+	for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
+		const V yv = *reinterpret_cast<const V*>(yp + i);
+		V av[NC];
+#pragma unroll
+		for (int k = 0; k < NC; ++k) av[k] = M::ld_nc(ap[k] + i);
+#pragma unroll
+		for (int k = 0; k < NC; ++k)
+#pragma unroll
+			for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][v]);
+	}
+#pragma unroll
+	for (int k = 0; k < NC; ++k) {
+		T s = acc[k][0];
+#pragma unroll
+		for (int v = 1; v < VN; ++v) s = s + acc[k][v];
+		s = warp_butterfly_sum(s);
+		if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
+	}
+}
 
+// ysm: y staged in shared memory by book2_prologue (nullptr: read d.y through L1/L2)
+template <typename T>
+__device__ void price_phase_direct(const Dev<T>& d, Smem& sh, const T* ysm, int part, int nparts) {
+	const int tid = threadIdx.x;
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 
-	// groups of PRICE_NC columns handed out by the ticket counter (first group = CTA index), like the tiles of
-	// the update pass: fast and slow SMs even out, results do not depend on who prices a column
 	const long long c1 = d.nsl;
-	const long long ngroups = (c1 + PRICE_NC - 1) / PRICE_NC;
+	const long long tail = d.price_tail < c1 ? d.price_tail : c1;
+	const long long nq = (c1 - tail) / PRICE_NC;              // full groups
+	const long long nitems = nq + (c1 - nq * PRICE_NC);       // + single columns
 	int buf = 0;
-	for (long long g = part; g < ngroups; buf ^= 1) {
-		const long long col = g * PRICE_NC;
+	for (long long g = part; g < nitems; buf ^= 1) {
 		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // read after the barrier below
-		const T* ap[PRICE_NC];
-#pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k) {
-			const long long cc = col + k < c1 ? col + k : c1 - 1;   // ragged tail: re-read the last column
-			ap[k] = d.A + cc * ld;
-		}
-		T acc[PRICE_NC][VN];
-#pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k)
-#pragma unroll
-			for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
-
-#pragma unroll 4
-		for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
-			const V yv = *reinterpret_cast<const V*>(d.y + i);
-			V av[PRICE_NC];
-#pragma unroll
-			for (int k = 0; k < PRICE_NC; ++k) av[k] = M::ld_nc(ap[k] + i);
-#pragma unroll
-			for (int k = 0; k < PRICE_NC; ++k)
-#pragma unroll
-				for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][v]);
-		}
-#pragma unroll
-		for (int k = 0; k < PRICE_NC; ++k) {
-			T s = acc[k][0];
-#pragma unroll
-			for (int v = 1; v < VN; ++v) s = s + acc[k][v];
-			s = warp_butterfly_sum(s);
-			if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
-		}
+		const bool quad = g < nq;
+		const long long col = quad ? g * PRICE_NC : nq * PRICE_NC + (g - nq);
+		if (quad) price_columns<T, PRICE_NC, 4>(d, sh, ysm, col, buf);
+		else      price_columns<T, 1, 16>(d, sh, ysm, col, buf);
 		__syncthreads();
 		g = sh.tk;
-		if (tid < PRICE_NC && col + tid < c1) {
+		if (tid < (quad ? PRICE_NC : 1)) {
 			T s = (T)sh.wsum[buf][tid][0];
 #pragma unroll
 			for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
@@ -591,11 +621,12 @@ __device__ void price_phase_direct(const Dev<T>& d, Smem& sh, int part, int npar
 			const double e = (double)(s - d.c[j]);
 			if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
 		}
-		__syncthreads();                              // sh.tk is rewritten at the top of the next group
+		__syncthreads();                              // sh.tk is rewritten at the top of the next item
 	}
 
+	const T* yp = ysm ? ysm : d.y;
 	for (long long k = d.k0 + (long long)part * NT + tid; k < d.k1; k += (long long)nparts * NT) {   // unit (slack) columns
-		const double e = (double)(d.y[k] - d.c[d.ns + k]);
+		const double e = (double)(yp[k] - d.c[d.ns + k]);
 		const long long j = d.ns + k;
 		if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
 	}
@@ -606,13 +637,77 @@ __device__ void price_phase_direct(const Dev<T>& d, Smem& sh, int part, int npar
 
 // ---------------------------------------------------------------- phase: update + FTRAN
 
+// alpha_i = sum over the FTRAN chunks of alpha_part[ck][i], strictly left to right; the loads of
+// 16 chunks are issued together (predicated, no serial remainder), only the adds are ordered
+template <typename T>
+__device__ __forceinline__ T sum_chunk_partials(const T* part0, long long stride, int nchunk) {
+	T a = __ldcg(part0);
+	for (int c0 = 1; c0 < nchunk; c0 += 16) {
+		T v[16];
+#pragma unroll
+		for (int u = 0; u < 16; ++u) v[u] = c0 + u < nchunk ? __ldcg(part0 + (long long)(c0 + u) * stride) : T(0);
+#pragma unroll
+		for (int u = 0; u < 16; ++u)
+			if (c0 + u < nchunk) a = a + v[u];
+	}
+	return a;
+}
+
+
+template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int r);
+
+// Ratio test of one finished row group (v4:199-208, 311-325): alpha of the group's rows = sum of their chunk
+// partials (left to right), stored into every rank's alpha vector (one rank: our own), masked (theta, index)
+// argmin over alpha > pivot_tol + eligible count -> rcand[g] / rcnt[g].  Run by the CTA that completed the
+// group's last tile while the other CTAs keep streaming B^-1.
+template <typename T>
+__device__ void finish_row_group(const Dev<T>& d, Smem& sh, long long g, long long grows) {
+	const int tid = threadIdx.x;
+	double best_v = CUDART_INF;
+	long long best_i = LLONG_MAX;
+	long long elig = 0;
+	const T tol = (T)d.pivot_tol;
+	for (long long r = tid; r < grows; r += NT) {
+		const long long il = g * grows + r;
+		if (il >= d.ldb) break;
+		const T a = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
+		const long long i = d.row0 + il;
+		for (int k = 0; k < d.nranks; ++k) xalpha(d, k)[i] = a;
+		if (i < d.m && a > tol) {
+			++elig;
+			const double th = (double)(d.x_b[i] / a);
+			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+		}
+	}
+	block_argmin(best_v, best_i, sh);
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) elig += __shfl_xor_sync(0xffffffffu, elig, off);
+	__syncthreads();
+	if ((tid & 31) == 0) sh.red_c[tid >> 5] = elig;
+	__syncthreads();
+	if (tid == 0) {
+		long long c = 0;
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) c += sh.red_c[w];
+		d.rcand[g].val = best_v;
+		d.rcand[g].idx = best_i;
+		d.rcnt[g] = c;
+	}
+}
+
 // One pass over B^-1:  (UPDATE) B^-1 += E_q (x) row_q   [cublasSger, v4:333]
 //                      (FTRAN)  alpha = B^-1_new a_p     [cublasSgemv, v4:307-308 of the NEXT iteration]
 // Thread owns VN consecutive rows (one 16-byte vector), a warp 32*VN rows, the
 // CTA's 8 warps are arranged WR (rows) x WC (columns) over a tile of
 // WR*32*VN rows x CHUNK columns.  row_q[chunk] and a_p[chunk] are staged in
 // shared memory.  alpha_part[chunk][row] receives the chunk partial.
-template <typename T, int WC, bool UPDATE, bool FTRAN>
+// Tiles are handed out row group by row group (d.rg row tiles = 256+ rows; inside a group the row tile runs
+// fastest, then the chunk).  FINISH: a CTA counts its tile on the group's counter; whoever completes the group
+// sums its chunk partials and runs the ratio test of its rows (finish_row_group) — the ratio test of the
+// reference (v4:311-325) needs neither a phase nor a grid barrier of its own.  The count of tile k is posted
+// (fence + atomic by one thread) after the staging barrier of tile k+1 and looked at after tile k+1 has been
+// streamed, so neither the fence nor the atomic's round trip is ever waited for; only a CTA's last tile pays it.
+template <typename T, int WC, bool UPDATE, bool FTRAN, bool FINISH>
 __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn, const T* acol, long long uk, bool reverse, int part, int nparts) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
@@ -628,6 +723,10 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	const long long ld = d.ldb, m = d.m;   // local row block
 	const long long ntr = (ld + TR - 1) / TR;
 	const long long ntiles = ntr * d.nchunk;
+	const long long RG = d.rg;                               // row tiles per (full) group
+	const long long tpg = RG * d.nchunk;                     // tiles per full group
+	const long long ngrp = (ntr + RG - 1) / RG;
+	const long long rgl = ntr - (ngrp - 1) * RG;             // row tiles of the last group
 	// staging area in dynamic shared memory (aliases the idle pricing ring): row_q chunk, a_p chunk, combine
 	T* stage_rq = reinterpret_cast<T*>(dyn);
 	T* stage_a = reinterpret_cast<T*>(dyn + CHUNK * 8);
@@ -639,9 +738,16 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	// the tiles backwards, so the part of B^-1 that is still in L2 from the previous pass (up to
 	// the L2 capacity, dirty lines included) is touched first and never makes the trip to HBM.
 	long long ticket = part;
+	long long prev_grp = -1;               // group of the tile this CTA finished last, not yet counted
+	unsigned int prev_target = 0, prev_done = 0;
+	constexpr int POSTER = 32;             // the thread that posts tile counts (warp 1, lane 0; thread 0 draws the tickets)
 	while (ticket < ntiles) {
 		const long long tile = reverse ? ntiles - 1 - ticket : ticket;
-		const long long rt = tile % ntr, ck = tile / ntr;
+		long long grp = tile / tpg;
+		if (grp >= ngrp) grp = ngrp - 1;
+		const long long rem = tile - grp * tpg;
+		const long long rgg = grp == ngrp - 1 ? rgl : RG;     // row tiles of this group
+		const long long rt = grp * RG + rem % rgg, ck = rem / rgg;
 		const long long j0 = ck * CHUNK;
 		__syncthreads();
 		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->upd_ctr, 1u);
@@ -657,6 +763,12 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 		}
 		__syncthreads();
 		const long long next_ticket = sh.tk;
+		if (FINISH && prev_grp >= 0 && tid == POSTER) {
+			// the alpha_part stores of the previous tile (any thread) happened before the two barriers above;
+			// this fence makes them visible at gpu scope before the count (they were issued a round trip ago)
+			__threadfence();
+			prev_done = atomicAdd(&d.grp_done[prev_grp], 1u) + 1u;
+		}
 
 		const long long row = rt * TR + (long long)wr * 32 * VN + (long long)lane * VN;
 		const bool active = row < ld;     // warp uniform (ld is a multiple of 32*VN)
@@ -756,24 +868,36 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 				}
 			}
 		}
+		if (FINISH) {
+			if (prev_grp >= 0) {               // CTA uniform
+				if (tid == POSTER) {
+					const bool last = prev_done == prev_target;
+					if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }   // acquire side: the group's partials are complete at L2
+					sh.bc_c = last;
+				}
+				__syncthreads();
+				const bool fin = sh.bc_c != 0;
+				__syncthreads();
+				if (fin) finish_row_group<T>(d, sh, prev_grp, RG * TR);
+			}
+			prev_grp = grp;
+			prev_target = (unsigned int)(rgg * d.nchunk);
+		}
 		ticket = next_ticket;
 	}
-}
-
-// alpha_i = sum over the FTRAN chunks of alpha_part[ck][i], strictly left to right; the loads of
-// 16 chunks are issued together (predicated, no serial remainder), only the adds are ordered
-template <typename T>
-__device__ __forceinline__ T sum_chunk_partials(const T* part0, long long stride, int nchunk) {
-	T a = __ldcg(part0);
-	for (int c0 = 1; c0 < nchunk; c0 += 16) {
-		T v[16];
-#pragma unroll
-		for (int u = 0; u < 16; ++u) v[u] = c0 + u < nchunk ? __ldcg(part0 + (long long)(c0 + u) * stride) : T(0);
-#pragma unroll
-		for (int u = 0; u < 16; ++u)
-			if (c0 + u < nchunk) a = a + v[u];
+	if (FINISH && prev_grp >= 0) {             // this CTA's last tile: post and look at once
+		__syncthreads();
+		if (tid == POSTER) {
+			__threadfence();
+			const bool last = atomicAdd(&d.grp_done[prev_grp], 1u) + 1u == prev_target;
+			if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }
+			sh.bc_c = last;
+		}
+		__syncthreads();
+		const bool fin = sh.bc_c != 0;
+		__syncthreads();
+		if (fin) finish_row_group<T>(d, sh, prev_grp, RG * TR);
 	}
-	return a;
 }
 
 // ---------------------------------------------------------------- phase: ratio test
@@ -795,7 +919,7 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 		} else {
 			a = d.alpha[i];   // already exchanged between the ranks
 		}
-		if (a > T(0)) {
+		if (a > (T)d.pivot_tol) {
 			++elig;
 			const double th = (double)(d.x_b[i] / a);
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
@@ -857,16 +981,16 @@ __device__ void book1_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 
 // ---------------------------------------------------------------- phase: bookkeeping 2
 
-// x_b += (row_q.b) E_q (v4:348);  y += ((c_b_new.E_q) + (c_p - c_b_q)) row_q (v4:355-356);
-// c_b[q] = c[p], b_ixs[q] = p (v4:340-342)
+// the two scalars of the linear updates: s_x = row_q.b (v4:347), s_y = c_b_new.E_q + (c_p - c_b_q) (v4:354-355);
+// slice partials summed left to right (loads of 32 slices together).  Valid in every thread afterwards.
 template <typename T>
-__device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
+__device__ __forceinline__ void book2_scalars(const Dev<T>& d, Smem& sh, long long p, T& sx, T& sy) {
 	const int tid = threadIdx.x;
 	__syncthreads();
 	if (tid < 2) {
 		T a = T(0);
 		const T* part = tid == 0 ? d.dpart0 : d.dpart + d.nslice;
-		for (int s0 = 0; s0 < d.nslice; s0 += 32) {      // loads of 32 slices together, adds left to right
+		for (int s0 = 0; s0 < d.nslice; s0 += 32) {
 			T v[32];
 #pragma unroll
 			for (int u = 0; u < 32; ++u) v[u] = s0 + u < d.nslice ? __ldcg(part + s0 + u) : T(0);
@@ -878,7 +1002,17 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 		sh.bc_s[tid] = (double)a;
 	}
 	__syncthreads();
-	const T sx = (T)sh.bc_s[0], sy = (T)sh.bc_s[1];
+	sx = (T)sh.bc_s[0];
+	sy = (T)sh.bc_s[1];
+}
+
+// x_b += (row_q.b) E_q (v4:348);  y += ((c_b_new.E_q) + (c_p - c_b_q)) row_q (v4:355-356);
+// c_b[q] = c[p], b_ixs[q] = p (v4:340-342)
+template <typename T>
+__device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
+	const int tid = threadIdx.x;
+	T sx, sy;
+	book2_scalars<T>(d, sh, p, sx, sy);
 	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
 		const T eq = d.E_q[i], rq = __ldcg(d.row_q + i);
 		d.x_b[i] = fma_t(sx, eq, d.x_b[i]);
@@ -886,6 +1020,44 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 		if (i == q) { d.c_b[i] = d.c[p]; d.b_ixs[i] = (int)p; }
 	}
 	fence_proxy_async_global();     // y is read by TMA (async proxy) in the next pricing phase
+}
+
+// The same updates as the PROLOGUE of the next pricing pass (d.fuse_book2: y fits in shared memory).  Every CTA
+// builds the whole new y in shared memory (ysm, ld elements) from the old y and row_q — the pricing pass then
+// reads y from there and never from L1/L2 — and applies its slice of the x_b / c_b / b_ixs updates in global
+// memory.  The global y is NOT touched here (other CTAs may still be reading the old one): y_flush does it after
+// the pricing barrier.  apply = false: no pivot pending, ysm = y.  Returns s_y for y_flush.
+template <typename T>
+__device__ T book2_prologue(const Dev<T>& d, Smem& sh, T* ysm, bool apply, long long p, long long q, int part, int nparts) {
+	using V = typename VecT<T>::V;
+	constexpr int VN = VecT<T>::N;
+	const int tid = threadIdx.x;
+	T sx = T(0), sy = T(0);
+	if (apply) {
+		book2_scalars<T>(d, sh, p, sx, sy);
+		for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
+			d.x_b[i] = fma_t(sx, d.E_q[i], d.x_b[i]);
+			if (i == q) { d.c_b[i] = d.c[p]; d.b_ixs[i] = (int)p; }
+		}
+	}
+	for (long long i = (long long)tid * VN; i < d.ld; i += (long long)NT * VN) {
+		V yv = __ldcg(reinterpret_cast<const V*>(d.y + i));
+		if (apply) {
+			const V rq = __ldcg(reinterpret_cast<const V*>(d.row_q + i));
+#pragma unroll
+			for (int v = 0; v < VN; ++v) Mem<T>::set(yv, v, fma_t(sy, Mem<T>::get(rq, v), Mem<T>::get(yv, v)));
+		}
+		*reinterpret_cast<V*>(ysm + i) = yv;
+	}
+	__syncthreads();
+	return sy;
+}
+
+// global y += s_y row_q for this CTA's slice; legal once every CTA is past its pricing pass (nobody reads the old y)
+template <typename T>
+__device__ __forceinline__ void y_flush(const Dev<T>& d, T sy, int part, int nparts) {
+	for (long long i = (long long)part * NT + threadIdx.x; i < d.m; i += (long long)nparts * NT)
+		d.y[i] = fma_t(sy, __ldcg(d.row_q + i), d.y[i]);
 }
 
 // z = c_b . x_b in slice order (v4:365); single CTA
@@ -912,6 +1084,12 @@ __device__ double objective(const Dev<T>& d, Smem& sh) {
 
 // The whole loop of v4:286-359 on the device.  Every CTA takes the same
 // branches because every decision is recomputed from the same global data.
+// Three grid barriers per pivot:
+//   price (+ prologue: x_b / y / c_b / b_ixs of the previous pivot when d.fuse_book2)   | B1 -> p, optimality
+//   update + FTRAN (+ ratio test of every row group as it completes)                     | B2 -> q, unboundedness
+//   book1 (row_q, E_q, dot partials)                                                     | B3
+// Without fuse_book2 (y does not fit in shared memory, or the TMA-ring pricing path reads it from global memory)
+// book2 stays a phase of its own with a fourth barrier.
 template <typename T, int WC>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	__shared__ Smem sh;
@@ -925,62 +1103,72 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	long long it = ctl->iter, pivots = ctl->pivots;
 	const long long it_end = ctl->it_end;
 	int pending = ctl->pending;
-	int status = 0, done = 0;
+	int status = 0, done = 0, aborted = 0;
 	long long p = ctl->p, q = ctl->q;
 	double min_e = ctl->min_e;
+	const bool fuse = d.fuse_book2 != 0;
+	T* ysm = reinterpret_cast<T*>(ringbuf);
+	bool pend2 = false;                 // book2 of the last pivot still to be applied (fuse only; never across launches)
+	T sy_keep = T(0);
 
 	const long long it0 = it;
 	while (it < it_end) {
 		// ---- pricing + entering column (v4:288-302)
 		stamp(d, it - it0, 0);
-		if (d.price_direct) price_phase_direct<T>(d, sh, me, G);
-		else                price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		if (fuse) {
+			sy_keep = book2_prologue<T>(d, sh, ysm, pend2, p, q, me, G);
+			price_phase_direct<T>(d, sh, ysm, me, G);
+		} else if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, me, G);
+		else                       price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
 		stamp(d, it - it0, 1);
-		grid_barrier(ctl, epoch);
+		if (me == 0 && threadIdx.x == 0) ctl->abort_latched = *(volatile int*)&ctl->abort_req;   // before CTA 0 arrives: one value for all
+		grid_barrier(ctl, epoch, G);
 		if (me == 0 && threadIdx.x == 0) ctl->price_ctr = 0;     // every CTA is past pricing; next use is barriers away
 		reduce_cands(d.cand, G, min_e, p, sh);
+		if (pend2) { y_flush<T>(d, sy_keep, me, G); pend2 = false; }   // read again two barriers from here at the earliest
 		stamp(d, it - it0, 2);
+		if (__ldcg(&ctl->abort_latched)) { aborted = 1; break; }
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
-		// ---- pending rank-1 update fused with the FTRAN of column p
+		// ---- pending rank-1 update fused with the FTRAN of column p and the ratio test (v4:333, 307-308, 311-325)
 		const T* acol = p < d.ns ? d.A + p * d.ld : nullptr;
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+		if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
 		pending = 0;
 		stamp(d, it - it0, 3);
-		grid_barrier(ctl, epoch);
+		grid_barrier(ctl, epoch, G);
 		if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
 		stamp(d, it - it0, 4);
-
-		// ---- ratio test (v4:311-325)
-		ratio_phase<T, true>(d, sh, me, G);
-		stamp(d, it - it0, 5);
-		grid_barrier(ctl, epoch);
 		double th;
-		reduce_cands(d.cand, G, th, q, sh);
-		const long long elig = reduce_counts(d.cnt, G, sh);
+		reduce_cands(d.rcand, d.ngrp, th, q, sh);
+		const long long elig = reduce_counts(d.rcnt, d.ngrp, sh);
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
-		stamp(d, it - it0, 6);
+		stamp(d, it - it0, 5);
 
 		// ---- pivot (v4:331-356)
 		book1_phase<T>(d, sh, p, q, me, G);
+		stamp(d, it - it0, 6);
+		grid_barrier(ctl, epoch, G);
 		stamp(d, it - it0, 7);
-		grid_barrier(ctl, epoch);
-		stamp(d, it - it0, 8);
-		book2_phase<T>(d, sh, p, q, me, G);
 		if (me == 0 && threadIdx.x == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
+		if (fuse && it + 1 < it_end) {
+			pend2 = true;               // rides in the prologue of the next pricing pass
+		} else {
+			book2_phase<T>(d, sh, p, q, me, G);
+			stamp(d, it - it0, 8);
+			grid_barrier(ctl, epoch, G);
+			stamp(d, it - it0, 9);
+		}
 		pending = 1;
 		++pivots;
-		stamp(d, it - it0, 9);
 		++it;
-		grid_barrier(ctl, epoch);
 	}
 
 	if (me == 0) {
 		const double z = objective<T>(d, sh);
 		if (threadIdx.x == 0) {
 			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
-			ctl->status = status; ctl->done = done;
+			ctl->status = status; ctl->done = done; ctl->aborted = aborted;
 			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
 		}
 	}
@@ -1125,7 +1313,7 @@ __global__ void __launch_bounds__(NT, 1) simplex_tiny(Dev<T> d) {
 		long long elig = 0;
 		for (int i = tid; i < m; i += NT) {
 			const T a = sal[i];
-			if (a > T(0)) {
+			if (a > (T)d.pivot_tol) {
 				++elig;
 				const double th = (double)(sx[i] / a);
 				if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
@@ -1250,12 +1438,12 @@ __device__ __forceinline__ bool wait_flag_sys(const unsigned long long* flag, un
 }
 
 // local grid barrier with a time-out (a CTA that gave up on a dead peer must not hang the others)
-__device__ __forceinline__ bool grid_barrier_t(Ctl* ctl, unsigned long long& epoch, Smem& sh) {
-	epoch += gridDim.x;
+__device__ __forceinline__ bool grid_barrier_t(Ctl* ctl, unsigned long long& epoch, Smem& sh, int G) {
+	epoch += G;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		bool ok = true;
-		if (gridDim.x > 1) {
+		if (G > 1) {
 			asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(&ctl->bar) : "memory");
 			if (ld_acquire_gpu(&ctl->bar) < epoch) {
 				const unsigned long long t0 = globaltimer_ns();
@@ -1314,12 +1502,15 @@ __device__ __forceinline__ bool gather_records(const Dev<T>& d, const XCand* rec
 	return ok;
 }
 
-// the last CTA of this rank reduces the per-CTA candidates and stores the record into every mailbox
+// the last CTA of this rank reduces the rank's candidates (per CTA for pricing, per row group for the ratio
+// test) and stores the record into every mailbox.  cnts == nullptr: the count field carries `extra`
+// (X1: this rank's abort request, so that all ranks stop in the same iteration).
 template <typename T>
-__device__ __forceinline__ void publish(const Dev<T>& d, Smem& sh, int which, int par, unsigned long long e, bool with_counts) {
+__device__ __forceinline__ void publish(const Dev<T>& d, Smem& sh, int which, int par, unsigned long long e,
+		const Cand* cands, int ncand, const long long* cnts, long long extra) {
 	double v; long long i;
-	reduce_cands(d.cand, gridDim.x, v, i, sh);
-	const long long c = with_counts ? reduce_counts(d.cnt, gridDim.x, sh) : 0;
+	reduce_cands(cands, ncand, v, i, sh);
+	const long long c = cnts ? reduce_counts(cnts, ncand, sh) : extra;
 	if (threadIdx.x < d.nranks) {
 		XHdr* h = xhdr(d, threadIdx.x);
 		XCand* dst = which == 0 ? &h->pc[par][d.rank] : &h->rc[d.rank];
@@ -1342,40 +1533,6 @@ __device__ void fetch_column(const Dev<T>& d, long long p, int part, int nparts)
 	const T* src = d.A_peer[o] + (p - d.colstart[o]) * d.ld;
 	for (long long i = ((long long)part * NT + threadIdx.x) * VN; i < d.ld; i += (long long)nparts * NT * VN)
 		*reinterpret_cast<V*>(d.acol + i) = M::ld_nc(src + i);
-}
-
-// X2 producer: alpha of the local rows = sum of the chunk partials (left to right), stored into
-// every rank's alpha; the ratio test of those rows (v4:199-208) gives this CTA's candidate.
-template <typename T>
-__device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, int part, int nparts) {
-	const int tid = threadIdx.x;
-	double best_v = CUDART_INF;
-	long long best_i = LLONG_MAX;
-	long long elig = 0;
-	for (long long il = (long long)part * NT + tid; il < d.ldb; il += (long long)nparts * NT) {
-		const T a = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
-		const long long i = d.row0 + il;
-		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
-		if (i < d.m && a > T(0)) {
-			++elig;
-			const double th = (double)(d.x_b[i] / a);
-			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
-		}
-	}
-	block_argmin(best_v, best_i, sh);
-#pragma unroll
-	for (int off = 16; off >= 1; off >>= 1) elig += __shfl_xor_sync(0xffffffffu, elig, off);
-	__syncthreads();
-	if ((tid & 31) == 0) sh.red_c[tid >> 5] = elig;
-	__syncthreads();
-	if (tid == 0) {
-		long long c = 0;
-#pragma unroll
-		for (int w = 0; w < NWARP; ++w) c += sh.red_c[w];
-		d.cand[part].val = best_v;
-		d.cand[part].idx = best_i;
-		d.cnt[part] = c;
-	}
 }
 
 // book1, sharded: E_q and the c_b.E_q slice partials on every rank (replicated data);
@@ -1418,14 +1575,15 @@ __device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long 
 	}
 }
 
+// One rank's loop.  G / me: size of this rank's CTA group and the CTA's index in it (the whole grid on a real
+// multi-GPU run; a slice of the grid when several ranks are emulated on one device).
+// Per pivot: X1 after pricing, the entering column fetch + one local barrier, the update + FTRAN pass whose row
+// groups push their alpha slices to every rank and run their ratio test as they complete, X2 (one record per
+// rank), book1 + local barrier + X3, book2 + local barrier.
 template <typename T, int WC>
-__global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T> d) {
-	__shared__ Smem sh;
-	extern __shared__ __align__(128) unsigned char ringbuf[];
-	Ring rcons, rprod;
-	ring_init(sh, rcons, rprod, d.price_nc);
+__device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, Ring& rcons, Ring& rprod, const int G, const int me) {
 	Ctl* ctl = d.ctl;
-	const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
+	const int tid = threadIdx.x;
 	unsigned long long epoch = 0;
 	unsigned long long xe = ctl->xepoch;            // serial number of the last pricing round
 	unsigned long long n1 = 0, n2 = 0;              // arrival targets of X1 / X2 in this launch
@@ -1433,7 +1591,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 	long long it = ctl->iter, pivots = ctl->pivots;
 	const long long it_end = ctl->it_end;
 	int pending = ctl->pending;
-	int status = 0, done = 0, bad = 0;
+	int status = 0, done = 0, bad = 0, aborted = 0;
 	long long p = ctl->p, q = ctl->q;
 	double min_e = ctl->min_e;
 	const XHdr* mine = xhdr(d, d.rank);
@@ -1441,61 +1599,62 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 	const long long it0 = it;
 	while (it < it_end) {
 		// ---- pricing over the local column block; X1
-		stamp(d, it - it0, 0);
+		stamp(d, it - it0, 0, me);
 		++xe;
 		const int par = (int)(xe & 1);
-		if (d.price_direct) price_phase_direct<T>(d, sh, me, G);
+		if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, me, G);
 		else                price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
-		stamp(d, it - it0, 1);
-		if (arrive_last(&ctl->xarr[0], n1 += G, sh)) publish(d, sh, 0, par, xe, false);
-		long long dummy;
-		if (!gather_records(d, mine->pc[par], xe, sh, min_e, p, dummy)) { bad = 1; break; }
+		stamp(d, it - it0, 1, me);
+		if (arrive_last(&ctl->xarr[0], n1 += G, sh))
+			publish(d, sh, 0, par, xe, d.cand, G, nullptr, (long long)*(volatile int*)&ctl->abort_req);
+		long long stop;
+		if (!gather_records(d, mine->pc[par], xe, sh, min_e, p, stop)) { bad = 1; break; }
 		if (me == 0 && tid == 0) ctl->price_ctr = 0;       // every local CTA is past pricing
-		stamp(d, it - it0, 2);
+		stamp(d, it - it0, 2, me);
+		if (stop > 0) { aborted = 1; break; }              // some rank was asked to stop: all ranks see the same sum
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
-		// ---- entering column from its owner, then the fused update + FTRAN on the local rows
+		// ---- entering column from its owner, then the fused update + FTRAN + ratio test on the local rows
 		const bool dense = p < d.ns;
 		if (dense) {
 			fetch_column<T>(d, p, me, G);
-			if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
+			if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
 		}
-		stamp(d, it - it0, 3);
-		if (pending) update_ftran_phase<T, WC, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		stamp(d, it - it0, 3, me);
+		if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
 		pending = 0;
-		stamp(d, it - it0, 4);
-		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
-		if (me == 0 && tid == 0) ctl->upd_ctr = 0;
-		stamp(d, it - it0, 5);
+		stamp(d, it - it0, 4, me);
 
-		// ---- X2: alpha slices to every rank together with the ratio test of the local rows (v4:311-325)
-		push_alpha_ratio<T>(d, sh, me, G);
-		if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, true);
+		// ---- X2: the row groups have stored their alpha slices into every rank and left their candidates;
+		// the last CTA to arrive publishes the rank's record (v4:311-325)
+		if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, d.rcand, d.ngrp, d.rcnt, 0);
 		double th;
 		long long elig;
 		if (!gather_records(d, mine->rc, xe, sh, th, q, elig)) { bad = 1; break; }
-		stamp(d, it - it0, 6);
+		if (me == 0 && tid == 0) ctl->upd_ctr = 0;         // every local CTA has left the update pass
+		stamp(d, it - it0, 5, me);
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
 
 		// ---- pivot: E_q everywhere, X3 row q from its owner, then the replicated O(m) updates
 		book1_sharded<T>(d, sh, p, q, me, G);
-		stamp(d, it - it0, 7);
-		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
+		stamp(d, it - it0, 6, me);
+		if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
 		// owner: the row and its partials were stored by all local CTAs before the barrier; one
 		// system-scope release covers them (release is cumulative over what the barrier acquired)
 		if (me == 0 && tid < d.nranks && q >= d.row0 && q < d.row0 + d.ldb) st_release_sys(&xhdr(d, tid)->rflag, xe);
 		if (tid == 0) sh.bc_c = wait_flag_sys(&mine->rflag, xe);
 		__syncthreads();
 		if (!sh.bc_c) { bad = 1; break; }
-		stamp(d, it - it0, 8);
+		stamp(d, it - it0, 7, me);
 		book2_phase<T>(d, sh, p, q, me, G);
 		if (me == 0 && tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
 		pending = 1;
 		++pivots;
-		stamp(d, it - it0, 9);
+		stamp(d, it - it0, 8, me);
 		++it;
-		if (!grid_barrier_t(ctl, epoch, sh)) { bad = 1; break; }
+		if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
+		stamp(d, it - 1 - it0, 9, me);
 	}
 
 	if (bad) { if (tid == 0) ctl->bad = 1; return; }
@@ -1503,10 +1662,34 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T
 		const double z = objective<T>(d, sh);
 		if (tid == 0) {
 			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
-			ctl->status = status; ctl->done = done; ctl->xepoch = xe;
+			ctl->status = status; ctl->done = done; ctl->xepoch = xe; ctl->aborted = aborted;
 			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
 		}
 	}
+}
+
+template <typename T, int WC>
+__global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T> d) {
+	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char ringbuf[];
+	Ring rcons, rprod;
+	ring_init(sh, rcons, rprod, d.price_nc);
+	sharded_loop<T, WC>(d, sh, ringbuf, rcons, rprod, gridDim.x, blockIdx.x);
+}
+
+// Several ranks on ONE device (tests on a single-GPU box, b200lp_create_multi with a repeated device): the
+// ranks' CTA groups are slices of one cooperative grid, so they are co-resident by construction — separate
+// launches that spin on each other must never share a GPU.  Same loop, same mailboxes, same flags; the "peer"
+// pointers are plain device pointers.  R ranks x (gridDim.x / R) CTAs.
+template <typename T, int WC>
+__global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded_emu(const Dev<T>* devs, int R) {
+	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char ringbuf[];
+	const int Gr = gridDim.x / R;
+	const Dev<T>& d = devs[blockIdx.x / Gr];
+	Ring rcons, rprod;
+	ring_init(sh, rcons, rprod, d.price_nc);
+	sharded_loop<T, WC>(d, sh, ringbuf, rcons, rprod, Gr, blockIdx.x % Gr);
 }
 
 // ---------------------------------------------------------------- stand-alone phase kernels
@@ -1519,7 +1702,7 @@ __global__ void __launch_bounds__(NT) k_price(Dev<T> d) {
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
 	ring_init(sh, rcons, rprod, d.price_nc);
-	if (d.price_direct) price_phase_direct<T>(d, sh, blockIdx.x, gridDim.x);
+	if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, blockIdx.x, gridDim.x);
 	else                price_phase<T>(d, sh, ringbuf, rcons, rprod, blockIdx.x, gridDim.x);
 }
 
@@ -1541,7 +1724,7 @@ template <typename T, int WC, bool UPDATE, bool FTRAN>
 __global__ void __launch_bounds__(NT) k_update_ftran(Dev<T> d, long long p, int reverse) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char dyn[];
-	update_ftran_phase<T, WC, UPDATE, FTRAN>(d, sh, dyn, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
+	update_ftran_phase<T, WC, UPDATE, FTRAN, false>(d, sh, dyn, p < d.ns ? d.A + p * d.ld : nullptr, p - d.ns, reverse != 0, blockIdx.x, gridDim.x);
 }
 
 // alpha_part <- chunk partials of B^-1 v for an arbitrary device vector v (length ld): the FTRAN pass alone
@@ -1549,7 +1732,14 @@ template <typename T, int WC>
 __global__ void __launch_bounds__(NT) k_ftran_vec(Dev<T> d, const T* v) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char dyn[];
-	update_ftran_phase<T, WC, false, true>(d, sh, dyn, v, 0, false, blockIdx.x, gridDim.x);
+	update_ftran_phase<T, WC, false, true, false>(d, sh, dyn, v, 0, false, blockIdx.x, gridDim.x);
+}
+
+// out[il] = sum of the chunk partials of local row il (left to right), il < ldb
+template <typename T>
+__global__ void __launch_bounds__(NT) k_sum_partials(Dev<T> d, T* out) {
+	for (long long il = (long long)blockIdx.x * NT + threadIdx.x; il < d.ldb; il += (long long)gridDim.x * NT)
+		out[il] = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
 }
 
 template <typename T>

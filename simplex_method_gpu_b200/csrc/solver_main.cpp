@@ -1,5 +1,5 @@
 // CLI with the driver contract of the reference's main() (src/v4_cub_reduction.cu:384-474):
-//   solver.out <lp.txt | lp.b200lp> [--f64] [--eps E] [--max-iter N] [--device D]
+//   solver.out <lp.txt | lp.b200lp> [--f64] [--eps E] [--max-iter N] [--device D] [--gpus N | --devices a,b,..]
 // Same input text format (v4:401-420; parsed by b200lp_read_lp, which also accepts the binary twin), same stdout: one "# Iteration k" line per
 // iteration (v4:287), the result block (v4:426-445) and the timing block
 // (v4:456-471, same labels and number format).  Defaults reproduce the reference's
@@ -29,6 +29,8 @@ static void print_time(const char* label, double s) {
 	std::cout << std::fixed << std::setprecision(2) << std::setw(6) << s << '\n';
 }
 
+static std::vector<int32_t> g_devices;   // --gpus / --devices: more than one entry = the sharded multi-GPU solve
+
 template <typename T>
 static int run(const char* path, b200lp_options opt, Clock::time_point t_start) {
 	// the reference allocates its pinned host arrays first and then parses into them (v4:407-420);
@@ -48,7 +50,14 @@ static int run(const char* path, b200lp_options opt, Clock::time_point t_start) 
 	auto t_solve = Clock::now();
 	b200lp_result r;
 	int rc;
-	if (sizeof(T) == 8)
+	if (g_devices.size() > 1) {
+		if (sizeof(T) == 8)
+			rc = b200lp_solve_f64_multi((const double*)A, (const double*)b, (const double*)c, m, n, &opt, g_devices.data(),
+					(int32_t)g_devices.size(), (double*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
+		else
+			rc = b200lp_solve_f32_multi((const float*)A, (const float*)b, (const float*)c, m, n, &opt, g_devices.data(),
+					(int32_t)g_devices.size(), (float*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
+	} else if (sizeof(T) == 8)
 		rc = b200lp_solve_f64((const double*)A, (const double*)b, (const double*)c, m, n, &opt,
 				(double*)x_b.data(), b_ixs.data(), nullptr, 0, &r);
 	else
@@ -115,11 +124,24 @@ int main(int argc, char* argv[]) {
 		else if (!std::strcmp(argv[i], "--eps") && i + 1 < argc) opt.eps = std::atof(argv[++i]);
 		else if (!std::strcmp(argv[i], "--max-iter") && i + 1 < argc) opt.max_iter = std::atoll(argv[++i]);
 		else if (!std::strcmp(argv[i], "--device") && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+		else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) {
+			g_devices.clear();
+			for (int k = 0, nk = std::atoi(argv[++i]); k < nk; ++k) g_devices.push_back(k);
+		}
+		else if (!std::strcmp(argv[i], "--devices") && i + 1 < argc) {
+			g_devices.clear();
+			for (const char* p = argv[++i]; *p;) {
+				g_devices.push_back((int32_t)std::strtol(p, const_cast<char**>(&p), 10));
+				if (*p == ',') ++p;
+				else if (*p) { std::cerr << "Bad device list.\n"; return 1; }
+			}
+		}
 		else {
 			std::cerr << "Unknown option " << argv[i] << "\n";
 			return 1;
 		}
 	}
 
+	if (g_devices.size() == 1) opt.device = g_devices[0];
 	return f64 ? run<double>(argv[1], opt, t_start) : run<float>(argv[1], opt, t_start);
 }

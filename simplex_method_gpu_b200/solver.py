@@ -84,8 +84,9 @@ def _prep(A, b, c, dtype):
 
 
 def solve(A, b, c, eps: float = EPS, max_iter: int = MAX_ITER, dtype=None, device: int = 0,
-          trace_cap: int | None = None, **opts) -> Solution:
-    """Drop-in for the reference's ``solve()`` (v4:219): host arrays in, host arrays out."""
+          trace_cap: int | None = None, devices=None, **opts) -> Solution:
+    """Drop-in for the reference's ``solve()`` (v4:219): host arrays in, host arrays out.
+    ``devices``: list of CUDA ordinals -> b200lp_solve_*_multi (B^-1 row-sharded, A column-sharded over them)."""
     A, b, c, m, n, dt = _prep(A, b, c, dtype)
     L = capi.lib()
     o = capi.default_options(eps=eps, max_iter=int(max_iter), device=device, **opts)
@@ -94,8 +95,14 @@ def solve(A, b, c, eps: float = EPS, max_iter: int = MAX_ITER, dtype=None, devic
     b_ixs = np.zeros(m, np.int32)
     trace = np.full((max(cap, 1), 2), -1, np.int32)
     res = capi.Result()
-    fn = L.b200lp_solve_f64 if dt == np.float64 else L.b200lp_solve_f32
-    capi.check(fn(_vp(A), _vp(b), _vp(c), m, n, C.byref(o), _vp(x_b), _vp(b_ixs), _vp(trace), cap, C.byref(res)))
+    if devices is not None:
+        devs = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+        fn = L.b200lp_solve_f64_multi if dt == np.float64 else L.b200lp_solve_f32_multi
+        capi.check(fn(_vp(A), _vp(b), _vp(c), m, n, C.byref(o), devs, len(devices), _vp(x_b), _vp(b_ixs), _vp(trace), cap,
+                      C.byref(res)))
+    else:
+        fn = L.b200lp_solve_f64 if dt == np.float64 else L.b200lp_solve_f32
+        capi.check(fn(_vp(A), _vp(b), _vp(c), m, n, C.byref(o), _vp(x_b), _vp(b_ixs), _vp(trace), cap, C.byref(res)))
     k = min(res.pivots, cap)
     return Solution(res.z, SolveStatus(res.status), x_b, b_ixs, res.iterations, res.pivots, trace[:k].copy(),
                     res.ms_upload, res.ms_solve, res.ms_download, res.kernel_launches, res.min_reduced_cost)
@@ -110,12 +117,18 @@ class Engine:
     """Handle API: device state survives between calls (benchmark windows, phase tests)."""
 
     def __init__(self, m: int, n: int, dtype=np.float64, eps: float = EPS, max_iter: int = MAX_ITER,
-                 device: int = 0, **opts):
+                 device: int = 0, devices=None, **opts):
+        """``devices``: list of CUDA ordinals -> one handle over several GPUs of this process (b200lp_create_multi)."""
         self.m, self.n, self.dtype = int(m), int(n), np.dtype(dtype)
         self._L = capi.lib()
         self._o = capi.default_options(eps=eps, max_iter=int(max_iter), device=device, **opts)
         self._h = C.c_void_p()
-        capi.check(self._L.b200lp_create(_dtype_code(self.dtype), self.m, self.n, C.byref(self._o), C.byref(self._h)))
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+            capi.check(self._L.b200lp_create_multi(_dtype_code(self.dtype), self.m, self.n, devs, len(devices),
+                                                   C.byref(self._o), C.byref(self._h)))
+        else:
+            capi.check(self._L.b200lp_create(_dtype_code(self.dtype), self.m, self.n, C.byref(self._o), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -149,7 +162,8 @@ class Engine:
 
     # -- loop
     def _result(self, res) -> dict:
-        return {"status": SolveStatus(res.status), "iterations": res.iterations, "pivots": res.pivots, "z": res.z,
+        return {"status": SolveStatus(res.status), "aborted": bool(res.aborted), "iterations": res.iterations,
+                "pivots": res.pivots, "z": res.z,
                 "min_reduced_cost": res.min_reduced_cost, "ms_solve": res.ms_solve, "ms_upload": res.ms_upload,
                 "kernel_launches": res.kernel_launches}
 
@@ -165,6 +179,10 @@ class Engine:
         res = capi.Result()
         capi.check(self._L.b200lp_wait(self._h, C.byref(res)))
         return self._result(res)
+
+    def abort(self):
+        """Ask a running loop to stop at its next iteration boundary (b200lp_abort); pair with wait()."""
+        capi.check(self._L.b200lp_abort(self._h))
 
     # -- results
     def download(self):

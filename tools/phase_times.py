@@ -27,6 +27,9 @@ ap.add_argument("--shape", type=int, default=0, help="update+FTRAN tile shape (w
 ap.add_argument("--price-cols", type=int, default=0)
 ap.add_argument("--l2", type=int, default=-1, help="l2_persist_mb: -1 off, 0 max, else MiB")
 ap.add_argument("--price-mode", type=int, default=0, help="0 auto, 1 TMA ring, 2 register-staged")
+ap.add_argument("--group-rows", type=int, default=0, help="ratio_group_rows (0 = auto)")
+ap.add_argument("--tail", type=int, default=0, help="price_tail: 0 auto, -1 none, else columns")
+ap.add_argument("--fuse", type=int, default=0, help="fuse_book2: 0 auto, -1 off")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 a.m, a.n = (int(x) for x in a.lp.lower().split("x"))
@@ -43,13 +46,15 @@ if world > 1:
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     e = ShardedEngine(a.m, a.n, np.float64, rank=rank, world=world, device=local, eps=1e-9, max_iter=1 << 30,
-                      profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode)
+                      profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode,
+                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse)
     e.generate_dense(1)
     e.connect()
     dist.barrier()
     names = names["sharded"]
 else:
-    e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode)
+    e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode,
+                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse)
     e.generate_dense(1)
     names = names["single"]
 
@@ -60,8 +65,9 @@ st = e.profile().astype(np.int64)         # (iterations, stamps)
 piv = r["pivots"] - r0["pivots"]
 k = len(names)
 st = st[a.skip:, :k]
-ok = (st > 0).all(axis=1)
-st = st[ok]
+st = st[st[:, 0] > 0]
+for j in range(1, k):                     # a point the loop did not pass (fused book2): zero-length interval
+    st[:, j] = np.where(st[:, j] == 0, st[:, j - 1], st[:, j])
 # stamp j of iteration i+1 closes the last interval of iteration i
 nxt = np.roll(st[:, 0], -1)
 full = np.concatenate([st, nxt[:, None]], axis=1)[:-1]
