@@ -71,7 +71,10 @@ typedef struct {
 	int32_t price_tail;   /* columns at the end of a pricing pass handed out one at a time: 0 = auto, -1 = none, else count */
 	int32_t fuse_book2;   /* x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass (3 grid barriers per
 	                         pivot instead of 4): 0 = auto (when y fits in shared memory), -1 = off */
-	int32_t reserved[4];
+	int32_t fuse_ratio;   /* ratio test of every row group inside the update+FTRAN pass as the group completes:
+	                         0 = auto (sharded engines only: there it also carries the alpha exchange), 1 = on,
+	                         -1 = off (a phase of its own after a grid barrier) */
+	int32_t reserved[3];
 } b200lp_options;
 
 typedef struct {

@@ -21,6 +21,10 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 MAX_ITER, OPTIMUM, UNBOUNDED, THETA_OVERFLOW = 0, 1, 2, 3
 
 
+class _Opts(C.Structure):
+    _fields_ = [("pivot_tol", C.c_double), ("harris_delta", C.c_double), ("ratio_mode", C.c_int), ("pricing_rule", C.c_int)]
+
+
 class _Result(C.Structure):
     _fields_ = [("status", C.c_int), ("iterations", C.c_long), ("pivots", C.c_long), ("z", C.c_double)]
 
@@ -43,11 +47,11 @@ def lib() -> C.CDLL:
         if not os.path.exists(_LIB_PATH):
             build()
         L = C.CDLL(_LIB_PATH)
-        for name, real in (("oracle_solve_f64", C.c_double), ("oracle_solve_f32", C.c_float)):
+        for name, real in (("oracle_solve_ex_f64", C.c_double), ("oracle_solve_ex_f32", C.c_float)):
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, real, C.c_long, C.c_int,
-                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.POINTER(_Opts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(_Result)]
         L.lpgen_u01.restype = C.c_double
         L.lpgen_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
@@ -89,8 +93,11 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=None) -> OracleSolution:
-    """A: (m, n) array in Fortran (column-major) order, dtype float32/float64; slack block last."""
+def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=None,
+          pivot_tol=0.0, ratio_mode=0, harris_delta=0.0, pricing_rule=0) -> OracleSolution:
+    """A: (m, n) array in Fortran (column-major) order, dtype float32/float64; slack block last.
+    pivot_tol / ratio_mode / harris_delta / pricing_rule: the modes outside the reference's contract
+    (simplex_oracle.h); all zero = the reference's loop."""
     dt = np.dtype(A.dtype)
     assert dt in (np.float32, np.float64)
     A = np.asfortranarray(A, dtype=dt)
@@ -107,8 +114,9 @@ def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=Non
     gp = np.zeros(cap, np.float64)
     gq = np.zeros(cap, np.float64)
     res = _Result()
-    fn = lib().oracle_solve_f64 if dt == np.float64 else lib().oracle_solve_f32
-    rc = fn(_ptr(A), _ptr(b), _ptr(c), m, n, eps, int(max_iter), int(order),
+    fn = lib().oracle_solve_ex_f64 if dt == np.float64 else lib().oracle_solve_ex_f32
+    opts = _Opts(float(pivot_tol), float(harris_delta), int(ratio_mode), int(pricing_rule))
+    rc = fn(_ptr(A), _ptr(b), _ptr(c), m, n, eps, int(max_iter), int(order), C.byref(opts),
             _ptr(x_b), _ptr(b_ixs), _ptr(y), _ptr(Binv), _ptr(tp), _ptr(tq), _ptr(gp), _ptr(gq), cap, C.byref(res))
     if rc != 0:
         raise ValueError(f"oracle_solve failed with code {rc} (m={m}, n={n})")

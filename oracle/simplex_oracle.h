@@ -27,6 +27,28 @@ typedef struct {
 } oracle_result;
 
 /*
+ * Modes outside the reference's parity contract; all zero = the reference's loop.
+ * The engine implements the same rules with the same arithmetic (include/b200lp.h: pivot_tol, ratio_mode,
+ * harris_delta, pricing_rule), so engine and oracle stay comparable pivot for pivot in every mode.
+ *   pivot_tol ....... ratio-test eligibility alpha > pivot_tol instead of alpha > 0 (v4:203; README.md:30
+ *                     "division by a small number")
+ *   ratio_mode ...... 0 textbook (v4:199-208); 1 bounded: theta = max(x_b, 0) / alpha (README.md:29 "what if
+ *                     x_b_t < 0"); 2 Harris two-pass: theta_max = min (max(x_b,0) + harris_delta) / alpha over
+ *                     the eligible rows, then the LARGEST alpha among rows with max(x_b,0)/alpha <= theta_max
+ *                     (lowest index on ties)
+ *   pricing_rule .... 0 Dantzig (v4:288-302); 1 steepest edge with the Goldfarb-Reid recurrence (README.md:16-17):
+ *                     p = argmax e_j^2 / gamma_j over e_j < -eps, gamma_j = 1 + |B^-1 a_j|^2 kept up to date with
+ *                     gamma_j <- max(gamma_j - 2 t_j (a_j . v) + t_j^2 gamma_p, 1 + t_j^2), t_j = (row_q . a_j) / alpha_q,
+ *                     v = B^-T alpha, gamma_p = 1 + alpha . alpha exact; optimality test unchanged (min e >= -eps)
+ */
+typedef struct {
+	double pivot_tol;
+	double harris_delta;
+	int ratio_mode;
+	int pricing_rule;
+} oracle_opts;
+
+/*
  * A is column-major m x n (v4:59-60), the slack/identity block is the LAST m
  * columns (v4:272-277).  order: 0 = plain left-to-right sums, 1 = the B200
  * engine's summation order.  Every output pointer may be NULL.
@@ -41,6 +63,18 @@ int oracle_solve_f64(const double* A, const double* b, const double* c, long m, 
 
 int oracle_solve_f32(const float* A, const float* b, const float* c, long m, long n,
 		float eps, long max_iter, int order,
+		float* x_b, int* b_ixs, float* y, float* Binv,
+		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
+		long trace_cap, oracle_result* res);
+
+/* the same with the optional modes above (opts == NULL: the reference's loop) */
+int oracle_solve_ex_f64(const double* A, const double* b, const double* c, long m, long n,
+		double eps, long max_iter, int order, const oracle_opts* opts,
+		double* x_b, int* b_ixs, double* y, double* Binv,
+		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
+		long trace_cap, oracle_result* res);
+int oracle_solve_ex_f32(const float* A, const float* b, const float* c, long m, long n,
+		float eps, long max_iter, int order, const oracle_opts* opts,
 		float* x_b, int* b_ixs, float* y, float* Binv,
 		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
 		long trace_cap, oracle_result* res);

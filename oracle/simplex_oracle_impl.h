@@ -119,12 +119,17 @@ static REAL FN(dot_sliced)(const REAL* x, const REAL* y, long n) {
 
 /* ---- the solver ------------------------------------------------------ */
 
-int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n,
-		REAL eps, long max_iter, int order,
+int FN(oracle_solve_ex)(const REAL* A, const REAL* b, const REAL* c, long m, long n,
+		REAL eps, long max_iter, int order, const oracle_opts* opts,
 		REAL* x_b_out, int* b_ixs_out, REAL* y_out, REAL* Binv_out,
 		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
 		long trace_cap, oracle_result* res) {
 	if (m <= 0 || n <= 0 || m > n) return -1;
+	/* modes outside the reference's contract (all zero = v4); see simplex_oracle.h */
+	const REAL pivot_tol = opts ? (REAL)opts->pivot_tol : (REAL)0;
+	const REAL harris_delta = opts ? (REAL)opts->harris_delta : (REAL)0;
+	const int ratio_mode = opts ? opts->ratio_mode : 0;
+	const int steepest = opts ? opts->pricing_rule == 1 : 0;
 
 	const long chunk = 256; /* engine FTRAN chunk width (order = 1) */
 	REAL* Binv = (REAL*)calloc((size_t)m * m, sizeof(REAL));
@@ -137,7 +142,10 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 	REAL* row_q = (REAL*)malloc(sizeof(REAL) * m);
 	REAL* E_q = (REAL*)malloc(sizeof(REAL) * m);
 	int* b_ixs = (int*)malloc(sizeof(int) * m);
+	REAL* gamma = steepest ? (REAL*)malloc(sizeof(REAL) * n) : NULL;   /* steepest-edge weights 1 + |B^-1 a_j|^2 */
+	REAL* vbt = steepest ? (REAL*)malloc(sizeof(REAL) * m) : NULL;     /* v = B^-T alpha */
 	if (!Binv || !c_b || !x_b || !y || !e || !alpha || !theta || !row_q || !E_q || !b_ixs) return -2;
+	if (steepest && (!gamma || !vbt)) return -2;
 
 	/* v4:272-277 */
 	for (long i = 0; i < m; ++i) {
@@ -156,6 +164,16 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 			for (long i = 0; i < m; ++i)
 				if (A[i + (n - m + j) * m] != (REAL)(i == j)) { ident = 0; break; }
 		if (ident) ns = n - m;
+	}
+
+	if (steepest) {
+		/* reference framework = the slack basis: B^-1 = I, gamma_j = 1 + |a_j|^2 (basic columns: never looked at) */
+		#pragma omp parallel for schedule(static)
+		for (long j = 0; j < n; ++j) {
+			const REAL* col = A + j * m;
+			if (j >= ns) gamma[j] = (REAL)2;
+			else gamma[j] = (REAL)1 + (order == 0 ? FN(dot_seq)(col, col, m, (REAL)0) : FN(dot_block256)(col, col, m));
+		}
 	}
 
 	int status = 0; /* MaxIter */
@@ -185,6 +203,18 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 			if (j != p && (double)e[j] - (double)min_val < gap_p) gap_p = (double)e[j] - (double)min_val;
 
 		if (min_val >= -eps) { status = 1; ++it; break; }
+
+		if (steepest) {
+			/* p = argmax e_j^2 / gamma_j over the attractive columns e_j < -eps, lowest index on ties */
+			REAL best = (REAL)-1, second = (REAL)-1;
+			for (long j = 0; j < n; ++j) {
+				if (!(e[j] < -eps)) continue;
+				const REAL sc = (e[j] * e[j]) / gamma[j];
+				if (sc > best) { second = best; best = sc; p = j; }
+				else if (sc > second) second = sc;
+			}
+			gap_p = second < (REAL)0 ? INFINITY : (double)best - (double)second;
+		}
 
 		/* ---- FTRAN, v4:307-308 ---- */
 		const REAL* a_p = A + p * m;
@@ -230,27 +260,53 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 			}
 		}
 
-		/* ---- ratio test, v4:199-208, 311-326 ---- */
+		/* ---- ratio test, v4:199-208, 311-326 (+ the optional modes) ---- */
 		long num_non_pos = 0;
 		for (long i = 0; i < m; ++i) {
-			int flag = alpha[i] > (REAL)0;
-			theta[i] = flag ? (x_b[i] / alpha[i]) : (REAL)INFINITY;
+			int flag = alpha[i] > pivot_tol;
+			const REAL xb = ratio_mode >= 1 && x_b[i] < (REAL)0 ? (REAL)0 : x_b[i];
+			theta[i] = flag ? (xb / alpha[i]) : (REAL)INFINITY;
 			num_non_pos += !flag;
 		}
 		if (num_non_pos == m) { status = 2; ++it; break; }
 		long q = 0;
-		REAL min_theta = theta[0];
-		for (long i = 1; i < m; ++i)
-			if (theta[i] < min_theta) { min_theta = theta[i]; q = i; }
 		double gap_q = INFINITY;
-		for (long i = 0; i < m; ++i)
-			if (i != q && (double)theta[i] - (double)min_theta < gap_q) gap_q = (double)theta[i] - (double)min_theta;
+		if (ratio_mode == 2) {
+			/* Harris: widest step the tolerance allows, then the largest pivot element inside it */
+			REAL theta_max = (REAL)INFINITY;
+			for (long i = 0; i < m; ++i) {
+				if (!(alpha[i] > pivot_tol)) continue;
+				const REAL xb = x_b[i] < (REAL)0 ? (REAL)0 : x_b[i];
+				const REAL t1 = (xb + harris_delta) / alpha[i];
+				if (t1 < theta_max) theta_max = t1;
+			}
+			REAL best_a = (REAL)-1;
+			for (long i = 0; i < m; ++i)
+				if (alpha[i] > pivot_tol && theta[i] <= theta_max && alpha[i] > best_a) { best_a = alpha[i]; q = i; }
+		} else {
+			REAL min_theta = theta[0];
+			for (long i = 1; i < m; ++i)
+				if (theta[i] < min_theta) { min_theta = theta[i]; q = i; }
+			for (long i = 0; i < m; ++i)
+				if (i != q && (double)theta[i] - (double)min_theta < gap_q) gap_q = (double)theta[i] - (double)min_theta;
+		}
 
 		if (pivots < trace_cap) {
 			if (trace_p) trace_p[pivots] = (int)p;
 			if (trace_q) trace_q[pivots] = (int)q;
 			if (trace_gap_p) trace_gap_p[pivots] = gap_p;
 			if (trace_gap_q) trace_gap_q[pivots] = gap_q;
+		}
+
+		REAL gamma_p = (REAL)0;
+		if (steepest) {
+			/* v = B^-T alpha with the inverse this pivot started from; gamma_p = 1 + |alpha|^2 exactly */
+			#pragma omp parallel for schedule(static)
+			for (long j = 0; j < m; ++j) {
+				const REAL* bc = Binv + j * m;
+				vbt[j] = order == 0 ? FN(dot_seq)(alpha, bc, m, (REAL)0) : FN(dot_block256)(bc, alpha, m);
+			}
+			gamma_p = (REAL)1 + (order == 0 ? FN(dot_seq)(alpha, alpha, m, (REAL)0) : FN(dot_sliced)(alpha, alpha, m));
 		}
 
 		/* ---- row extract + E_q + rank-1 update, v4:331-333 ---- */
@@ -267,8 +323,31 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 
 		/* ---- bookkeeping, v4:339-342 ---- */
 		const REAL c_b_q = c_b[q];
+		const long leaving = b_ixs[q];
 		c_b[q] = c[p];
 		b_ixs[q] = (int)p;
+
+		if (steepest) {
+			/* Goldfarb-Reid recurrence over every column (basic ones carry values nobody reads) */
+			#pragma omp parallel for schedule(static)
+			for (long j = 0; j < n; ++j) {
+				const REAL* col = A + j * m;
+				REAL r, w;
+				if (j >= ns) { r = row_q[j - ns]; w = vbt[j - ns]; }          /* recognised unit column */
+				else if (order == 0) { r = FN(dot_seq)(row_q, col, m, (REAL)0); w = FN(dot_seq)(vbt, col, m, (REAL)0); }
+				else { r = FN(dot_block256)(col, row_q, m); w = FN(dot_block256)(col, vbt, m); }
+				const REAL t = r / alpha_q;
+				const REAL g1 = FMA(t * t, gamma_p, FMA((REAL)-2 * t, w, gamma[j]));
+				const REAL g2 = FMA(t, t, (REAL)1);
+				gamma[j] = g1 > g2 ? g1 : g2;
+			}
+			{
+				const REAL ia = (REAL)1 / alpha_q;
+				const REAL g1 = gamma_p * (ia * ia), g2 = FMA(ia, ia, (REAL)1);
+				gamma[leaving] = g1 > g2 ? g1 : g2;
+				gamma[p] = (REAL)2;
+			}
+		}
 
 		/* ---- x_b, v4:347-348 ---- */
 		REAL s = order == 0 ? FN(dot_seq)(row_q, b, m, (REAL)0) : FN(dot_sliced)(row_q, b, m);
@@ -297,8 +376,17 @@ int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n
 	if (Binv_out) memcpy(Binv_out, Binv, sizeof(REAL) * (size_t)m * m);
 
 	free(Binv); free(c_b); free(x_b); free(y); free(e); free(alpha);
-	free(theta); free(row_q); free(E_q); free(b_ixs);
+	free(theta); free(row_q); free(E_q); free(b_ixs); free(gamma); free(vbt);
 	return 0;
+}
+
+int FN(oracle_solve)(const REAL* A, const REAL* b, const REAL* c, long m, long n,
+		REAL eps, long max_iter, int order,
+		REAL* x_b_out, int* b_ixs_out, REAL* y_out, REAL* Binv_out,
+		int* trace_p, int* trace_q, double* trace_gap_p, double* trace_gap_q,
+		long trace_cap, oracle_result* res) {
+	return FN(oracle_solve_ex)(A, b, c, m, n, eps, max_iter, order, NULL, x_b_out, b_ixs_out, y_out, Binv_out,
+		trace_p, trace_q, trace_gap_p, trace_gap_q, trace_cap, res);
 }
 
 #undef FN

@@ -3,6 +3,7 @@
 nvcc cross-compiles for sm_100a without a GPU.  Outputs:
   simplex_method_gpu_b200/libb200lp.so   C-ABI engine (include/b200lp.h)
   bin/solver.out                         CLI with the reference's main() contract
+  bin/solver_glpk.out                    solver_glpk.cpp-shaped CPU harness (links GLPK only where <glpk.h> exists)
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libb200lp.so")
 CLI_PATH = os.path.join(_ROOT, "bin", "solver.out")
+GLPK_PATH = os.path.join(_ROOT, "bin", "solver_glpk.out")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -52,6 +54,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
         cmd = [_nvcc(), "-O2", "-std=c++17", "-o", CLI_PATH, cli_src[0], "-I", os.path.join(_ROOT, "include"),
                "-L", _PKG, "-lb200lp", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../simplex_method_gpu_b200"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True, capture_output=not verbose)
+    glpk_src = os.path.join(_ROOT, "tools", "solver_glpk_harness.cpp")
+    if os.path.exists(glpk_src) and (force or _stale(GLPK_PATH, [glpk_src])):
+        os.makedirs(os.path.dirname(GLPK_PATH), exist_ok=True)
+        cxx = shutil.which("g++") or "g++"
+        have_glpk = any(os.path.exists(os.path.join(d, "glpk.h")) for d in ("/usr/include", "/usr/local/include"))
+        cmd = [cxx, "-O2", "-std=c++17", glpk_src, "-o", GLPK_PATH] + (["-lglpk"] if have_glpk else [])
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True, capture_output=not verbose)

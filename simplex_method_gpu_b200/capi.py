@@ -34,7 +34,8 @@ class Options(C.Structure):
                 ("tile_shape", C.c_int32), ("check_slack", C.c_int32), ("mode", C.c_int32), ("profile", C.c_int32),
                 ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32),
                 ("price_mode", C.c_int32), ("ratio_group_rows", C.c_int32), ("pivot_tol", C.c_double),
-                ("price_tail", C.c_int32), ("fuse_book2", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("price_tail", C.c_int32), ("fuse_book2", C.c_int32), ("fuse_ratio", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class Result(C.Structure):

@@ -203,13 +203,15 @@ public:
 			const long long ntr = (d.ldb + tr - 1) / tr;
 			const long long want = opt.ratio_group_rows > 0 ? opt.ratio_group_rows : 256;
 			d.rg = (int)std::max<long long>(1, want / tr);
-			d.ngrp = (int)std::max<long long>(1, (ntr + d.rg - 1) / d.rg);
+			d.ngrp = (int)((ntr + d.rg - 1) / d.rg);              // 0: this rank owns no rows (more ranks than row blocks)
 			CU(alloc(&d.rcand, (size_t)d.ngrp + 1));
 			CU(alloc(&d.rcnt, (size_t)d.ngrp + 1));
 			CU(alloc(&d.grp_done, (size_t)d.ngrp + 1));
 			CU(cudaMemsetAsync(d.grp_done, 0, ((size_t)d.ngrp + 1) * sizeof(unsigned int), stream));
 		}
 		d.pivot_tol = sizeof(T) == 4 ? (double)(float)opt.pivot_tol : opt.pivot_tol;
+		d.fuse_ratio = (opt.fuse_ratio > 0 || nranks > 1) ? 1 : 0;    // measured: pays only where it also carries an exchange
+		d.dbg = opt.reserved[0];
 		return B200LP_OK;
 	}
 

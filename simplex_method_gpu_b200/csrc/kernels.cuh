@@ -113,6 +113,8 @@ struct Dev {
 	unsigned int* grp_done;   // tiles finished per row group (reset by the finisher)
 	int rg;                   // row tiles per row group
 	int ngrp;                 // row groups of the local row block
+	int fuse_ratio;           // 1: ratio test per row group inside the update+FTRAN pass; 0: a phase of its own after a barrier
+	int dbg;                  // experiments (options.reserved[0])
 	int fuse_book2;           // 1: the O(m) updates of a pivot ride in the prologue of the next pricing pass (y in shared memory)
 	int price_tail;           // columns at the end of the local block priced one at a time (shorter tail of the pass)
 	double pivot_tol;         // ratio-test eligibility alpha > pivot_tol (0 = the reference's strict test, v4:203)
@@ -656,6 +658,20 @@ __device__ __forceinline__ T sum_chunk_partials(const T* part0, long long stride
 
 template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int r);
 
+// tile count of a row group: release at gpu scope (the tile's alpha_part stores, made by other threads of the
+// CTA before a barrier, are visible at L2 before the count is).  A release atom is one MEMBAR.ALL.GPU + ATOM;
+// __threadfence() would be an SC fence plus an L1 invalidation (MEMBAR.SC + ERRBAR + CCTL.IVALL) per tile.
+__device__ __forceinline__ unsigned int post_tile(unsigned int* ctr, int variant) {
+	unsigned int old;
+	if (variant == 1) {
+		__threadfence();
+		old = atomicAdd(ctr, 1u);
+	} else {
+		asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+	}
+	return old + 1u;
+}
+
 // Ratio test of one finished row group (v4:199-208, 311-325): alpha of the group's rows = sum of their chunk
 // partials (left to right), stored into every rank's alpha vector (one rank: our own), masked (theta, index)
 // argmin over alpha > pivot_tol + eligible count -> rcand[g] / rcnt[g].  Run by the CTA that completed the
@@ -701,12 +717,14 @@ __device__ void finish_row_group(const Dev<T>& d, Smem& sh, long long g, long lo
 // CTA's 8 warps are arranged WR (rows) x WC (columns) over a tile of
 // WR*32*VN rows x CHUNK columns.  row_q[chunk] and a_p[chunk] are staged in
 // shared memory.  alpha_part[chunk][row] receives the chunk partial.
-// Tiles are handed out row group by row group (d.rg row tiles = 256+ rows; inside a group the row tile runs
-// fastest, then the chunk).  FINISH: a CTA counts its tile on the group's counter; whoever completes the group
-// sums its chunk partials and runs the ratio test of its rows (finish_row_group) — the ratio test of the
-// reference (v4:311-325) needs neither a phase nor a grid barrier of its own.  The count of tile k is posted
-// (fence + atomic by one thread) after the staging barrier of tile k+1 and looked at after tile k+1 has been
-// streamed, so neither the fence nor the atomic's round trip is ever waited for; only a CTA's last tile pays it.
+// Tiles are handed out chunk by chunk, row tile fastest (measured: concurrent CTAs must sweep whole columns — a
+// group-major order that leaves only 2 KB of a column contiguous costs 8 % of the pass).  FINISH (row groups of
+// d.rg row tiles = 256+ rows): a CTA counts its tile on the group's counter; whoever completes the group sums its
+// chunk partials and runs the ratio test of its rows (finish_row_group), so the ratio test of the reference
+// (v4:311-325) needs neither a phase nor a grid barrier of its own.  The count of tile k is posted behind the
+// first loads of tile k+1 and looked at after tile k+1 has been streamed.  Measured on one GPU the release
+// (one MEMBAR.GPU round trip per tile in one warp, ~0.65 us per tile) costs more than the phase and barrier it
+// saves, so FINISH is used by the sharded loop only (there it also carries the alpha exchange).
 template <typename T, int WC, bool UPDATE, bool FTRAN, bool FINISH>
 __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn, const T* acol, long long uk, bool reverse, int part, int nparts) {
 	using M = Mem<T>;
@@ -723,10 +741,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	const long long ld = d.ldb, m = d.m;   // local row block
 	const long long ntr = (ld + TR - 1) / TR;
 	const long long ntiles = ntr * d.nchunk;
-	const long long RG = d.rg;                               // row tiles per (full) group
-	const long long tpg = RG * d.nchunk;                     // tiles per full group
-	const long long ngrp = (ntr + RG - 1) / RG;
-	const long long rgl = ntr - (ngrp - 1) * RG;             // row tiles of the last group
+	const long long RG = d.rg;                               // row tiles per row group (the last group may be shorter)
 	// staging area in dynamic shared memory (aliases the idle pricing ring): row_q chunk, a_p chunk, combine
 	T* stage_rq = reinterpret_cast<T*>(dyn);
 	T* stage_a = reinterpret_cast<T*>(dyn + CHUNK * 8);
@@ -743,11 +758,9 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	constexpr int POSTER = 32;             // the thread that posts tile counts (warp 1, lane 0; thread 0 draws the tickets)
 	while (ticket < ntiles) {
 		const long long tile = reverse ? ntiles - 1 - ticket : ticket;
-		long long grp = tile / tpg;
-		if (grp >= ngrp) grp = ngrp - 1;
-		const long long rem = tile - grp * tpg;
-		const long long rgg = grp == ngrp - 1 ? rgl : RG;     // row tiles of this group
-		const long long rt = grp * RG + rem % rgg, ck = rem / rgg;
+		const long long rt = tile % ntr, ck = tile / ntr;     // row tile fastest: concurrent CTAs sweep whole columns
+		const long long grp = rt / RG;
+		const long long rgg = ntr - grp * RG < RG ? ntr - grp * RG : RG;   // row tiles of this group
 		const long long j0 = ck * CHUNK;
 		__syncthreads();
 		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->upd_ctr, 1u);
@@ -763,12 +776,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 		}
 		__syncthreads();
 		const long long next_ticket = sh.tk;
-		if (FINISH && prev_grp >= 0 && tid == POSTER) {
-			// the alpha_part stores of the previous tile (any thread) happened before the two barriers above;
-			// this fence makes them visible at gpu scope before the count (they were issued a round trip ago)
-			__threadfence();
-			prev_done = atomicAdd(&d.grp_done[prev_grp], 1u) + 1u;
-		}
+		bool post = FINISH && prev_grp >= 0 && tid == POSTER;   // count the previous tile on its group (see below)
 
 		const long long row = rt * TR + (long long)wr * 32 * VN + (long long)lane * VN;
 		const bool active = row < ld;     // warp uniform (ld is a multiple of 32*VN)
@@ -870,6 +878,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 		}
 		if (FINISH) {
 			if (prev_grp >= 0) {               // CTA uniform
+				if (post) prev_done = post_tile(&d.grp_done[prev_grp], d.dbg);   // (inactive rows / ragged chunk: the fast path above was not taken)
 				if (tid == POSTER) {
 					const bool last = prev_done == prev_target;
 					if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }   // acquire side: the group's partials are complete at L2
@@ -888,8 +897,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	if (FINISH && prev_grp >= 0) {             // this CTA's last tile: post and look at once
 		__syncthreads();
 		if (tid == POSTER) {
-			__threadfence();
-			const bool last = atomicAdd(&d.grp_done[prev_grp], 1u) + 1u == prev_target;
+			const bool last = post_tile(&d.grp_done[prev_grp], d.dbg) == prev_target;
 			if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }
 			sh.bc_c = last;
 		}
@@ -1132,16 +1140,30 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 
 		// ---- pending rank-1 update fused with the FTRAN of column p and the ratio test (v4:333, 307-308, 311-325)
 		const T* acol = p < d.ns ? d.A + p * d.ld : nullptr;
-		if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
-		pending = 0;
-		stamp(d, it - it0, 3);
-		grid_barrier(ctl, epoch, G);
-		if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
-		stamp(d, it - it0, 4);
 		double th;
-		reduce_cands(d.rcand, d.ngrp, th, q, sh);
-		const long long elig = reduce_counts(d.rcnt, d.ngrp, sh);
+		long long elig;
+		if (d.fuse_ratio) {
+			if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			stamp(d, it - it0, 3);
+			grid_barrier(ctl, epoch, G);
+			if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
+			stamp(d, it - it0, 4);
+			reduce_cands(d.rcand, d.ngrp, th, q, sh);
+			elig = reduce_counts(d.rcnt, d.ngrp, sh);
+		} else {
+			if (pending) update_ftran_phase<T, WC, true, true, false>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			else         update_ftran_phase<T, WC, false, true, false>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			stamp(d, it - it0, 3);
+			grid_barrier(ctl, epoch, G);
+			if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
+			ratio_phase<T, true>(d, sh, me, G);
+			grid_barrier(ctl, epoch, G);
+			stamp(d, it - it0, 4);
+			reduce_cands(d.cand, G, th, q, sh);
+			elig = reduce_counts(d.cnt, G, sh);
+		}
+		pending = 0;
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
 		stamp(d, it - it0, 5);
 

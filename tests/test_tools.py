@@ -79,3 +79,23 @@ def test_solve_with_engine_needs_a_gpu(conv, engine_lib, capsys):
         assert rc == 0 and out.out == "x[1] = 1\nx[2] = 3\nOptimal objective: 9\n"
     else:
         assert rc == 2 and "no CUDA device" in out.err          # no CPU fallback behind --engine
+
+
+def test_glpk_harness_builds_and_degrades_loudly(conv, tmp_path):
+    """tools/solver_glpk_harness.cpp = solver_glpk.cpp's contract (/root/reference/solver_glpk.cpp:15-39), compiled
+    against GLPK only where <glpk.h> exists.  Here GLPK is absent: the binary must say so and exit 3 (never pretend);
+    where GLPK exists it must print the optimum of the sample LP like solver_glpk.cpp does."""
+    import subprocess
+    from simplex_method_gpu_b200 import _build
+    _build.build()
+    assert os.path.exists(_build.GLPK_PATH)
+    mps = str(tmp_path / "sample.mps")
+    assert conv.main(["to-mps", os.path.join(GOLDEN, "sample.txt"), mps]) == 0
+    r = subprocess.run([_build.GLPK_PATH, mps], capture_output=True, text=True, timeout=60)
+    have = any(os.path.exists(os.path.join(d, "glpk.h")) for d in ("/usr/include", "/usr/local/include"))
+    if have:
+        assert r.returncode == 0 and "Optimal objective: " in r.stdout
+        assert abs(abs(float(r.stdout.split("Optimal objective: ")[1].split()[0])) - 9.0) < 1e-9
+    else:
+        assert r.returncode == 3 and "built without GLPK" in r.stderr
+    assert subprocess.run([_build.GLPK_PATH], capture_output=True, text=True).returncode == 1
