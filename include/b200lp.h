@@ -72,9 +72,12 @@ typedef struct {
 	int32_t fuse_book2;   /* x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass (3 grid barriers per
 	                         pivot instead of 4): 0 = auto (when y fits in shared memory), -1 = off */
 	int32_t fuse_ratio;   /* ratio test of every row group inside the update+FTRAN pass as the group completes:
-	                         0 = auto (sharded engines only: there it also carries the alpha exchange), 1 = on,
-	                         -1 = off (a phase of its own after a grid barrier) */
-	int32_t reserved[3];
+	                         0 = auto (off: measured slower), 1 = on, -1 = off (the ratio test is a
+	                         phase of its own after a grid barrier) */
+	int32_t pricing_rule; /* 0 = Dantzig, the reference's rule (v4:288-302); 1 = steepest edge with the Goldfarb-Reid
+	                         recurrence (the reference's to-do list, README.md:16-17): a different pivot sequence, far
+	                         fewer pivots, one more read of B^-1 per pivot; single GPU, persistent kernel */
+	int32_t reserved[2];
 } b200lp_options;
 
 typedef struct {

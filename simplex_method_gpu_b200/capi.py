@@ -35,7 +35,7 @@ class Options(C.Structure):
                 ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32),
                 ("price_mode", C.c_int32), ("ratio_group_rows", C.c_int32), ("pivot_tol", C.c_double),
                 ("price_tail", C.c_int32), ("fuse_book2", C.c_int32), ("fuse_ratio", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("pricing_rule", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Result(C.Structure):

@@ -130,7 +130,15 @@ public:
 		CU(alloc(&hcst, (size_t)d.n));
 		d.c = hcst;
 		CU(alloc(&d.alpha_part, (size_t)d.nchunk * (size_t)d.ldb));
-		CU(alloc(&d.dpart, (size_t)2 * d.nslice));
+		CU(alloc(&d.dpart, (size_t)3 * d.nslice));
+		d.pricing_rule = opt.pricing_rule;
+		if (opt.pricing_rule == 1) {
+			if (nranks > 1) return fail(B200LP_ERR_ARG, "steepest-edge pricing (pricing_rule = 1) is single-GPU only");
+			if (opt.mode != 0) return fail(B200LP_ERR_ARG, "steepest-edge pricing needs the persistent kernel (mode = 0)");
+			CU(alloc(&d.gamma, (size_t)d.n));
+			CU(alloc(&d.vbt, ld));
+			CU(cudaMemsetAsync(d.vbt, 0, ld * sizeof(T), stream));
+		} else if (opt.pricing_rule != 0) return fail(B200LP_ERR_ARG, "pricing_rule must be 0 (Dantzig) or 1 (steepest edge)");
 		d.dpart0 = nranks > 1 ? d.row_q + ld : d.dpart;
 		CU(alloc(&d.b_ixs, m));
 		CU(alloc(&d.ctl, 1));
@@ -170,10 +178,13 @@ public:
 				(const void*)simplex_persistent<T, 4>, (const void*)simplex_persistent<T, 8>,
 				(const void*)simplex_persistent_sharded<T, 1>, (const void*)simplex_persistent_sharded<T, 2>,
 				(const void*)simplex_persistent_sharded<T, 4>, (const void*)simplex_persistent_sharded<T, 8>,
+				(const void*)simplex_persistent<T, 1, true>, (const void*)simplex_persistent<T, 2, true>,
+				(const void*)simplex_persistent<T, 4, true>, (const void*)simplex_persistent<T, 8, true>,
 				(const void*)k_price<T>})
 			CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_BYTES));
 		int occ = 0;
 		if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, DYN_SMEM_BYTES));
+		else if (opt.pricing_rule == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1, true>, NT, DYN_SMEM_BYTES));
 		else            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, DYN_SMEM_BYTES));
 		if (occ < 1) return fail(B200LP_ERR_CUDA, "persistent kernel does not fit on an SM");
 		max_grid = occ * num_sms;
@@ -185,6 +196,7 @@ public:
 		else g = num_sms * std::min(occ, 4);
 		grid = std::max(1, std::min(g, max_grid));
 		CU(alloc(&d.cand, (size_t)max_grid + 2));
+		CU(alloc(&d.cand2, (size_t)max_grid + 2));
 		CU(alloc(&d.cnt, (size_t)max_grid + 2));
 
 		// tile shape of the update+FTRAN pass: tiles are handed out dynamically, so the tallest row
@@ -210,7 +222,7 @@ public:
 			CU(cudaMemsetAsync(d.grp_done, 0, ((size_t)d.ngrp + 1) * sizeof(unsigned int), stream));
 		}
 		d.pivot_tol = sizeof(T) == 4 ? (double)(float)opt.pivot_tol : opt.pivot_tol;
-		d.fuse_ratio = (opt.fuse_ratio > 0 || nranks > 1) ? 1 : 0;    // measured: pays only where it also carries an exchange
+		d.fuse_ratio = opt.fuse_ratio > 0 ? 1 : 0;    // measured: the per-tile release costs more than the phase it saves
 		d.dbg = opt.reserved[0];
 		return B200LP_OK;
 	}
@@ -326,6 +338,10 @@ public:
 		if (int rc = settle()) return rc;
 		k_reset<T><<<num_sms * 8, 256, 0, stream>>>(d);
 		launches++;
+		if (opt.pricing_rule == 1) {                       // steepest edge: the weights start over with the slack basis
+			k_gamma_init<T><<<num_sms * 4, NT, 0, stream>>>(d);
+			launches++;
+		}
 		CU(cudaGetLastError());
 		const unsigned long long xe = hc.xepoch;    // the peer-barrier epoch outlives a reset
 		std::memset(&hc, 0, sizeof(hc));
@@ -368,6 +384,11 @@ public:
 			   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2>
 			   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4>
 			             : (const void*)simplex_persistent_sharded<T, 8>;
+		} else if (opt.pricing_rule == 1) {
+			fn = wc == 1 ? (const void*)simplex_persistent<T, 1, true>
+			   : wc == 2 ? (const void*)simplex_persistent<T, 2, true>
+			   : wc == 4 ? (const void*)simplex_persistent<T, 4, true>
+			             : (const void*)simplex_persistent<T, 8, true>;
 		} else {
 			fn = wc == 1 ? (const void*)simplex_persistent<T, 1>
 			   : wc == 2 ? (const void*)simplex_persistent<T, 2>
@@ -606,8 +627,10 @@ public:
 		return B200LP_OK;
 	}
 
+	// algorithmic bytes: B^-1 read + written once, the structural columns read once; steepest edge reads B^-1 once
+	// more (v = B^-T alpha)
 	int64_t bytes_per_pivot() const override {
-		return (int64_t)sizeof(T) * (2 * d.m * d.m + d.m * (d.n - d.m));
+		return (int64_t)sizeof(T) * ((opt.pricing_rule == 1 ? 3 : 2) * d.m * d.m + d.m * (d.n - d.m));
 	}
 
 	// ---- sharded mode: peer mapping of the A shards and mailboxes (CUDA IPC over NVLink) ----
@@ -666,6 +689,7 @@ private:
 		// TMA ring at 1 GB (8-GPU shard of m = 32768) and 8 GB; the ring is kept for the largest shards.
 		d.price_direct = opt.price_mode == 1 ? 0 : opt.price_mode == 2 ? 1
 		               : ((size_t)d.ld * (size_t)nsl_new * sizeof(T) <= ((size_t)2 << 30) ? 1 : 0);
+		if (opt.pricing_rule == 1) d.price_direct = 1;      // the steepest-edge pass is register-staged
 		// x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass: y must fit in the (idle) ring memory
 		// and pricing must read y from there (register-staged path); single GPU only
 		d.fuse_book2 = (opt.fuse_book2 >= 0 && nranks == 1 && d.price_direct && opt.mode == 0 &&
@@ -736,7 +760,7 @@ private:
 		Ctl* st = static_cast<Ctl*>(pinned);
 		*st = hc;
 		st->bar = 0;
-		st->price_ctr = st->upd_ctr = 0;
+		st->price_ctr = st->upd_ctr = st->btran_ctr = 0;
 		st->xarr[0] = st->xarr[1] = 0;
 		cudaError_t e = cudaMemcpyAsync(d.ctl, st, sizeof(Ctl), cudaMemcpyHostToDevice, stream);
 		if (e != cudaSuccess) return e;
@@ -785,7 +809,7 @@ private:
 	// tiny LPs (one warp-wide vector row, everything fits in shared memory): the shared-memory-resident kernel.
 	// Only with the automatic grid: an explicit grid_ctas asks for the general kernel.
 	bool tiny_ok() const {
-		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0) return false;
+		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0 || opt.pricing_rule != 0) return false;
 		if (d.ld != 32 * VecT<T>::N) return false;
 		return TinyLayout<T>(d.m, d.n, d.ns).bytes(d.m) <= (size_t)200 * 1024;
 	}

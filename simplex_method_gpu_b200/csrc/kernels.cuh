@@ -87,7 +87,11 @@ struct Ctl {
 	int abort_req;            // host: stop at the next iteration boundary (b200lp_abort); written while the kernel runs
 	int abort_latched;        // CTA 0's copy of abort_req, taken before it arrives at the pricing barrier
 	int aborted;              // the last launch ended because of abort_req
+	int se_pending;           // steepest edge: the weight recurrence of the last pivot is still to be applied
+	unsigned int btran_ctr;   // dynamic work tickets of the BTRAN pass (steepest edge)
 	int pad0;
+	long long leaving;        // steepest edge: variable that left the basis in the last pivot
+	double alpha_q;           // steepest edge: pivot element of the last pivot
 	long long p, q;           // last entering column / leaving row
 	double min_e;             // last pricing minimum
 	double c_b_q;             // c_b[q] before the swap (v4:339)
@@ -108,6 +112,10 @@ struct Dev {
 	int* b_ixs;               // m
 	Cand* cand;               // one per CTA
 	long long* cnt;           // eligible rows, one per CTA
+	Cand* cand2;              // steepest edge: per-CTA (-e^2/gamma, index) candidate
+	T* gamma;                 // steepest edge: weights 1 + |B^-1 a_j|^2 of all n columns
+	T* vbt;                   // steepest edge: v = B^-T alpha (ld)
+	int pricing_rule;         // 0 Dantzig (v4:288-302), 1 steepest edge with the Goldfarb-Reid recurrence (README.md:16-17)
 	Cand* rcand;              // ratio-test candidate of every row group of the update+FTRAN pass
 	long long* rcnt;          // eligible rows of every row group
 	unsigned int* grp_done;   // tiles finished per row group (reset by the finisher)
@@ -228,11 +236,11 @@ struct Smem {
 	double red_v[NWARP];
 	long long red_i[NWARP];
 	long long red_c[NWARP];
-	double wsum[2][PRICE_NC][NWARP];  // pricing: warp sums, double buffered
-	double dsum[2][NWARP];            // O(m) dots
+	double wsum[2][PRICE_NC * 3][NWARP];  // pricing: warp sums (steepest edge: three dots per column), double buffered
+	double dsum[3][NWARP];            // O(m) dots
 	double bc_v;                      // broadcasts
 	long long bc_c;
-	double bc_s[2];
+	double bc_s[3];
 	long long tk;                     // update_ftran: next dynamic tile
 	double xv[MAXR];                  // sharded: records gathered from the mailbox
 	long long xi[MAXR];
@@ -340,7 +348,7 @@ constexpr int NSTAMP = 16;
 	"{\"single\": [\"price (+ book2 prologue)\", \"barrier + argmin p\", \"update + FTRAN + ratio groups\", \"barrier\", " \
 	"\"argmin q\", \"book1 (row_q, E_q, dots)\", \"barrier\", \"book2 (x_b, y) [unfused only]\", \"barrier [unfused only]\", \"loop\"], " \
 	"\"sharded\": [\"price\", \"X1: arrive, publish candidate, gather\", \"fetch a_p + barrier\", " \
-	"\"update + FTRAN + ratio groups (alpha slices pushed)\", \"X2: arrive, publish, gather\", " \
+	"\"update + FTRAN\", \"X2: barrier, alpha + ratio of local rows, publish, gather\", " \
 	"\"book1 (E_q, dots; owner: row_q push)\", \"barrier + X3 flag\", \"book2 (x_b, y)\", \"barrier\", \"loop\"]}"
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -556,43 +564,57 @@ __device__ void price_phase(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, R
 // finishes its last item, and a single column is a quarter of a group (measured on 8 GPUs, m = 32768: a group is
 // ~40 us of a ~170 us pass).
 
-// dot products of NC consecutive columns with y: per-thread partial sums reduced to one value per warp in
-// sh.wsum[buf][k][warp].  UR row steps are unrolled so that NC * UR 16-byte loads are in flight per thread.
-template <typename T, int NC, int UR>
-__device__ __forceinline__ void price_columns(const Dev<T>& d, Smem& sh, const T* ysm, long long col, int buf) {
+// dot products of NC consecutive columns (base, leading dimension ldm, nrows rows) with NV vectors: per-thread
+// partial sums reduced to one value per warp in sh.wsum[buf][k * NV + w][warp].  UR row steps are unrolled so that
+// NC * UR 16-byte loads are in flight per thread.  COHERENT: the matrix is written by this kernel (B^-1), use the
+// coherent path; otherwise the read-only non-coherent one (A).  The summation order of every dot is the pricing
+// order of the file header, whatever NC / UR / NV.
+template <typename T, int NC, int UR, int NV, bool COHERENT>
+__device__ __forceinline__ void column_dots(const T* base, long long ldm, long long nrows, const T* const (&vec)[3], Smem& sh, int buf) {
 	using M = Mem<T>;
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const long long ld = d.ld;
-	const T* ap[NC];
-#pragma unroll
-	for (int k = 0; k < NC; ++k) ap[k] = d.A + (col + k) * ld;
-	const T* yp = ysm ? ysm : d.y;
-	T acc[NC][VN];
+	T acc[NC][NV][VN];
 #pragma unroll
 	for (int k = 0; k < NC; ++k)
 #pragma unroll
-		for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
+		for (int w = 0; w < NV; ++w)
+#pragma unroll
+			for (int v = 0; v < VN; ++v) acc[k][w][v] = T(0);
 #pragma unroll UR
-	for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
-		const V yv = *reinterpret_cast<const V*>(yp + i);
+	for (long long i = (long long)tid * VN; i < nrows; i += (long long)NT * VN) {
 		V av[NC];
 #pragma unroll
-		for (int k = 0; k < NC; ++k) av[k] = M::ld_nc(ap[k] + i);
+		for (int k = 0; k < NC; ++k) av[k] = COHERENT ? M::ld_stream(base + k * ldm + i) : M::ld_nc(base + k * ldm + i);
 #pragma unroll
-		for (int k = 0; k < NC; ++k)
+		for (int w = 0; w < NV; ++w) {
+			const V yv = *reinterpret_cast<const V*>(vec[w] + i);
 #pragma unroll
-			for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][v]);
+			for (int k = 0; k < NC; ++k)
+#pragma unroll
+				for (int v = 0; v < VN; ++v) acc[k][w][v] = fma_t(M::get(av[k], v), M::get(yv, v), acc[k][w][v]);
+		}
 	}
 #pragma unroll
-	for (int k = 0; k < NC; ++k) {
-		T s = acc[k][0];
+	for (int k = 0; k < NC; ++k)
 #pragma unroll
-		for (int v = 1; v < VN; ++v) s = s + acc[k][v];
-		s = warp_butterfly_sum(s);
-		if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
-	}
+		for (int w = 0; w < NV; ++w) {
+			T s = acc[k][w][0];
+#pragma unroll
+			for (int v = 1; v < VN; ++v) s = s + acc[k][w][v];
+			s = warp_butterfly_sum(s);
+			if (lane == 0) sh.wsum[buf][k * NV + w][warp] = (double)s;
+		}
+}
+
+// the 8 warp sums of dot `slot`, left to right
+template <typename T>
+__device__ __forceinline__ T warp_sums(const Smem& sh, int buf, int slot) {
+	T s = (T)sh.wsum[buf][slot][0];
+#pragma unroll
+	for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][slot][w];
+	return s;
 }
 
 // ysm: y staged in shared memory by book2_prologue (nullptr: read d.y through L1/L2)
@@ -611,14 +633,13 @@ __device__ void price_phase_direct(const Dev<T>& d, Smem& sh, const T* ysm, int 
 		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);   // read after the barrier below
 		const bool quad = g < nq;
 		const long long col = quad ? g * PRICE_NC : nq * PRICE_NC + (g - nq);
-		if (quad) price_columns<T, PRICE_NC, 4>(d, sh, ysm, col, buf);
-		else      price_columns<T, 1, 16>(d, sh, ysm, col, buf);
+		const T* const vec[3] = {ysm ? ysm : d.y, nullptr, nullptr};
+		if (quad) column_dots<T, PRICE_NC, 4, 1, false>(d.A + col * d.ld, d.ld, d.ld, vec, sh, buf);
+		else      column_dots<T, 1, 16, 1, false>(d.A + col * d.ld, d.ld, d.ld, vec, sh, buf);
 		__syncthreads();
 		g = sh.tk;
 		if (tid < (quad ? PRICE_NC : 1)) {
-			T s = (T)sh.wsum[buf][tid][0];
-#pragma unroll
-			for (int w = 1; w < NWARP; ++w) s = s + (T)sh.wsum[buf][tid][w];
+			const T s = warp_sums<T>(sh, buf, tid);
 			const long long j = d.col0 + col + tid;     // global column index
 			const double e = (double)(s - d.c[j]);
 			if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
@@ -635,6 +656,122 @@ __device__ void price_phase_direct(const Dev<T>& d, Smem& sh, const T* ysm, int 
 
 	block_argmin(best_v, best_i, sh);
 	if (tid == 0) { d.cand[part].val = best_v; d.cand[part].idx = best_i; }
+}
+
+// ---------------------------------------------------------------- steepest-edge pricing (README.md:16-17)
+//
+// p = argmax e_j^2 / gamma_j over the attractive columns e_j < -eps (lowest index on ties), gamma_j = 1 + |B^-1 a_j|^2
+// kept exact by the Goldfarb-Reid recurrence.  The recurrence of the PREVIOUS pivot rides in this pass: besides
+// e_j = y.a_j - c_j every column also gets  r_j = row_q.a_j  and  w_j = v.a_j  (v = B^-T alpha) from the same
+// bytes of A, then
+//     t = r_j / alpha_q,   gamma_j <- max(gamma_j - 2 t w_j + t^2 gamma_p, 1 + t^2),
+// the entering column of that pivot is set to 2 and its leaving variable to max(gamma_p / alpha_q^2, 1 + 1/alpha_q^2).
+// The optimality test is the reference's (min e_j >= -eps, v4:299), so both candidates are reduced.
+// Mirrored by the oracle (oracle/simplex_oracle_impl.h, pricing_rule = 1) with the same arithmetic.
+
+struct SeUpd {
+	bool on;                 // a pivot's recurrence is pending
+	long long p, leaving;    // its entering column / leaving variable (global column indices)
+	double alpha_q, gamma_p;
+};
+
+template <typename T>
+__device__ __forceinline__ T se_weight(const Dev<T>& d, const SeUpd& u, long long j, T r, T w) {
+	T g = d.gamma[j];
+	if (u.on) {
+		const T aq = (T)u.alpha_q, gp = (T)u.gamma_p;
+		if (j == u.p) g = T(2);
+		else if (j == u.leaving) {
+			const T ia = T(1) / aq;
+			const T g1 = gp * (ia * ia), g2 = fma_t(ia, ia, T(1));
+			g = g1 > g2 ? g1 : g2;
+		} else {
+			const T t = r / aq;
+			const T g1 = fma_t(t * t, gp, fma_t(T(-2) * t, w, g));
+			const T g2 = fma_t(t, t, T(1));
+			g = g1 > g2 ? g1 : g2;
+		}
+		d.gamma[j] = g;
+	}
+	return g;
+}
+
+// vec = {y, row_q, v}: shared-memory copies where they fit, global otherwise
+template <typename T>
+__device__ void price_phase_se(const Dev<T>& d, Smem& sh, const T* const (&vec)[3], const SeUpd& u, int part, int nparts) {
+	const int tid = threadIdx.x;
+	double best_v = CUDART_INF, se_v = CUDART_INF;      // (min e, index) and (min -e^2/gamma, index)
+	long long best_i = LLONG_MAX, se_i = LLONG_MAX;
+	const double neg_eps = -d.eps;
+	auto consider = [&](long long j, T e, T r, T w) {
+		const T g = se_weight<T>(d, u, j, r, w);
+		if (cand_better((double)e, j, best_v, best_i)) { best_v = (double)e; best_i = j; }
+		if ((double)e < neg_eps) {
+			const double sc = -(double)((e * e) / g);
+			if (cand_better(sc, j, se_v, se_i)) { se_v = sc; se_i = j; }
+		}
+	};
+
+	const long long c1 = d.nsl;
+	const long long nq = c1 / PRICE_NC;
+	const long long nitems = nq + (c1 - nq * PRICE_NC);
+	int buf = 0;
+	for (long long g = part; g < nitems; buf ^= 1) {
+		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->price_ctr, 1u);
+		const bool quad = g < nq;
+		const long long col = quad ? g * PRICE_NC : nq * PRICE_NC + (g - nq);
+		const T* base = d.A + col * d.ld;
+		if (u.on) {
+			if (quad) column_dots<T, PRICE_NC, 2, 3, false>(base, d.ld, d.ld, vec, sh, buf);
+			else      column_dots<T, 1, 8, 3, false>(base, d.ld, d.ld, vec, sh, buf);
+		} else {
+			if (quad) column_dots<T, PRICE_NC, 4, 1, false>(base, d.ld, d.ld, vec, sh, buf);
+			else      column_dots<T, 1, 16, 1, false>(base, d.ld, d.ld, vec, sh, buf);
+		}
+		__syncthreads();
+		g = sh.tk;
+		if (tid < (quad ? PRICE_NC : 1)) {
+			const long long j = d.col0 + col + tid;
+			const int nv = u.on ? 3 : 1;
+			const T e = warp_sums<T>(sh, buf, tid * nv) - d.c[j];
+			const T r = u.on ? warp_sums<T>(sh, buf, tid * nv + 1) : T(0);
+			const T w = u.on ? warp_sums<T>(sh, buf, tid * nv + 2) : T(0);
+			consider(j, e, r, w);
+		}
+		__syncthreads();
+	}
+	for (long long k = d.k0 + (long long)part * NT + tid; k < d.k1; k += (long long)nparts * NT)   // unit (slack) columns
+		consider(d.ns + k, vec[0][k] - d.c[d.ns + k], u.on ? vec[1][k] : T(0), u.on ? vec[2][k] : T(0));
+
+	block_argmin(best_v, best_i, sh);
+	block_argmin(se_v, se_i, sh);
+	if (tid == 0) {
+		d.cand[part].val = best_v; d.cand[part].idx = best_i;
+		d.cand2[part].val = se_v; d.cand2[part].idx = se_i;
+	}
+}
+
+// v = B^-T alpha: the column dots of B^-1 with alpha, in the pricing order (one extra read of B^-1 per pivot,
+// the price of exact steepest-edge weights).  Column groups come from ctl->btran_ctr.
+template <typename T>
+__device__ void btran_phase(const Dev<T>& d, Smem& sh, const T* alpha_vec, int part, int nparts) {
+	const int tid = threadIdx.x;
+	const long long c1 = d.m;
+	const long long nq = c1 / PRICE_NC;
+	const long long nitems = nq + (c1 - nq * PRICE_NC);
+	const T* const vec[3] = {alpha_vec, nullptr, nullptr};
+	int buf = 0;
+	for (long long g = part; g < nitems; buf ^= 1) {
+		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->btran_ctr, 1u);
+		const bool quad = g < nq;
+		const long long col = quad ? g * PRICE_NC : nq * PRICE_NC + (g - nq);
+		if (quad) column_dots<T, PRICE_NC, 4, 1, true>(d.B + col * d.ldb, d.ldb, d.ldb, vec, sh, buf);
+		else      column_dots<T, 1, 16, 1, true>(d.B + col * d.ldb, d.ldb, d.ldb, vec, sh, buf);
+		__syncthreads();
+		g = sh.tk;
+		if (tid < (quad ? PRICE_NC : 1)) d.vbt[col + tid] = warp_sums<T>(sh, buf, tid);
+		__syncthreads();
+	}
 }
 
 // ---------------------------------------------------------------- phase: update + FTRAN
@@ -724,7 +861,8 @@ __device__ void finish_row_group(const Dev<T>& d, Smem& sh, long long g, long lo
 // (v4:311-325) needs neither a phase nor a grid barrier of its own.  The count of tile k is posted behind the
 // first loads of tile k+1 and looked at after tile k+1 has been streamed.  Measured on one GPU the release
 // (one MEMBAR.GPU round trip per tile in one warp, ~0.65 us per tile) costs more than the phase and barrier it
-// saves, so FINISH is used by the sharded loop only (there it also carries the alpha exchange).
+// saves — 14 tiles per CTA at m = 8192, 55 on a 2-GPU shard of m = 32768 — so FINISH is an option
+// (options.fuse_ratio = 1), not the default, on one GPU and in the sharded loop alike.
 template <typename T, int WC, bool UPDATE, bool FTRAN, bool FINISH>
 __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn, const T* acol, long long uk, bool reverse, int part, int nparts) {
 	using M = Mem<T>;
@@ -955,30 +1093,37 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 // row_q = B^-1[q,:] (old), E_q from alpha (v4:331-332, 210-215) and the slice
 // partials of  row_q.b  (v4:347)  and  c_b_new.E_q  (v4:354; c_b[q] already
 // replaced by c[p], v4:340).
-template <typename T>
+// SE: also the slice partials of alpha.alpha (gamma_p = 1 + |alpha|^2) and the pivot's alpha_q / leaving variable
+template <typename T, bool SE = false>
 __device__ void book1_phase(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const T alpha_q = d.alpha[q];
 	const T c_p = d.c[p];
 	for (long long s = part; s < d.nslice; s += nparts) {
 		const long long i = s * SLICE + tid;
-		T t1 = T(0), t2 = T(0);
+		T t1 = T(0), t2 = T(0), t3 = T(0);
 		if (i < d.m) {
 			const T rq = d.B[q + i * d.ldb];
-			const T eq = (i != q) ? (-d.alpha[i] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			const T al = d.alpha[i];
+			const T eq = (i != q) ? (-al / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
 			d.row_q[i] = rq;
 			d.E_q[i] = eq;
 			T cb = d.c_b[i];
-			if (i == q) { d.ctl->c_b_q = (double)cb; cb = c_p; }
+			if (i == q) {
+				d.ctl->c_b_q = (double)cb; cb = c_p;
+				if (SE) { d.ctl->alpha_q = (double)alpha_q; d.ctl->leaving = d.b_ixs[q]; }
+			}
 			t1 = fma_t(rq, d.b[i], T(0));
 			t2 = fma_t(cb, eq, T(0));
+			if (SE) t3 = fma_t(al, al, T(0));
 		}
 		t1 = warp_butterfly_sum(t1);
 		t2 = warp_butterfly_sum(t2);
+		if (SE) t3 = warp_butterfly_sum(t3);
 		__syncthreads();
-		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; }
+		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; if (SE) sh.dsum[2][warp] = (double)t3; }
 		__syncthreads();
-		if (tid < 2) {
+		if (tid < (SE ? 3 : 2)) {
 			T a = T(0);
 #pragma unroll
 			for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[tid][w];
@@ -991,13 +1136,14 @@ __device__ void book1_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 
 // the two scalars of the linear updates: s_x = row_q.b (v4:347), s_y = c_b_new.E_q + (c_p - c_b_q) (v4:354-355);
 // slice partials summed left to right (loads of 32 slices together).  Valid in every thread afterwards.
-template <typename T>
-__device__ __forceinline__ void book2_scalars(const Dev<T>& d, Smem& sh, long long p, T& sx, T& sy) {
+// SE: also gamma_p = 1 + alpha.alpha of the last pivot (steepest edge).
+template <typename T, bool SE = false>
+__device__ __forceinline__ void book2_scalars(const Dev<T>& d, Smem& sh, long long p, T& sx, T& sy, T* gp = nullptr) {
 	const int tid = threadIdx.x;
 	__syncthreads();
-	if (tid < 2) {
+	if (tid < (SE ? 3 : 2)) {
 		T a = T(0);
-		const T* part = tid == 0 ? d.dpart0 : d.dpart + d.nslice;
+		const T* part = tid == 0 ? d.dpart0 : d.dpart + (long long)tid * d.nslice;
 		for (int s0 = 0; s0 < d.nslice; s0 += 32) {
 			T v[32];
 #pragma unroll
@@ -1007,11 +1153,13 @@ __device__ __forceinline__ void book2_scalars(const Dev<T>& d, Smem& sh, long lo
 				if (s0 + u < d.nslice) a = a + v[u];
 		}
 		if (tid == 1) a += d.c[p] - (T)__ldcg(&d.ctl->c_b_q);
+		if (tid == 2) a = T(1) + a;
 		sh.bc_s[tid] = (double)a;
 	}
 	__syncthreads();
 	sx = (T)sh.bc_s[0];
 	sy = (T)sh.bc_s[1];
+	if (SE && gp) *gp = (T)sh.bc_s[2];
 }
 
 // x_b += (row_q.b) E_q (v4:348);  y += ((c_b_new.E_q) + (c_p - c_b_q)) row_q (v4:355-356);
@@ -1035,14 +1183,16 @@ __device__ void book2_phase(const Dev<T>& d, Smem& sh, long long p, long long q,
 // reads y from there and never from L1/L2 — and applies its slice of the x_b / c_b / b_ixs updates in global
 // memory.  The global y is NOT touched here (other CTAs may still be reading the old one): y_flush does it after
 // the pricing barrier.  apply = false: no pivot pending, ysm = y.  Returns s_y for y_flush.
-template <typename T>
-__device__ T book2_prologue(const Dev<T>& d, Smem& sh, T* ysm, bool apply, long long p, long long q, int part, int nparts) {
+// SE (steepest edge): gp receives gamma_p; row_q and v are staged behind y while they fit (nstage = 1..3 vectors).
+template <typename T, bool SE = false>
+__device__ T book2_prologue(const Dev<T>& d, Smem& sh, T* ysm, bool apply, long long p, long long q, int part, int nparts,
+		T* gp = nullptr, int nstage = 1) {
 	using V = typename VecT<T>::V;
 	constexpr int VN = VecT<T>::N;
 	const int tid = threadIdx.x;
 	T sx = T(0), sy = T(0);
 	if (apply) {
-		book2_scalars<T>(d, sh, p, sx, sy);
+		book2_scalars<T, SE>(d, sh, p, sx, sy, gp);
 		for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
 			d.x_b[i] = fma_t(sx, d.E_q[i], d.x_b[i]);
 			if (i == q) { d.c_b[i] = d.c[p]; d.b_ixs[i] = (int)p; }
@@ -1056,6 +1206,8 @@ __device__ T book2_prologue(const Dev<T>& d, Smem& sh, T* ysm, bool apply, long 
 			for (int v = 0; v < VN; ++v) Mem<T>::set(yv, v, fma_t(sy, Mem<T>::get(rq, v), Mem<T>::get(yv, v)));
 		}
 		*reinterpret_cast<V*>(ysm + i) = yv;
+		if (SE && nstage > 1) *reinterpret_cast<V*>(ysm + d.ld + i) = __ldcg(reinterpret_cast<const V*>(d.row_q + i));
+		if (SE && nstage > 2) *reinterpret_cast<V*>(ysm + 2 * d.ld + i) = __ldcg(reinterpret_cast<const V*>(d.vbt + i));
 	}
 	__syncthreads();
 	return sy;
@@ -1098,7 +1250,9 @@ __device__ double objective(const Dev<T>& d, Smem& sh) {
 //   book1 (row_q, E_q, dot partials)                                                     | B3
 // Without fuse_book2 (y does not fit in shared memory, or the TMA-ring pricing path reads it from global memory)
 // book2 stays a phase of its own with a fourth barrier.
-template <typename T, int WC>
+// SE: steepest-edge pricing (price_phase_se), one more read of B^-1 per pivot for v = B^-T alpha (btran_phase, in
+// the same barrier interval as book1).
+template <typename T, int WC, bool SE = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
@@ -1118,12 +1272,29 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 	T* ysm = reinterpret_cast<T*>(ringbuf);
 	bool pend2 = false;                 // book2 of the last pivot still to be applied (fuse only; never across launches)
 	T sy_keep = T(0);
+	bool pendg = SE && ctl->se_pending != 0;   // steepest edge: weight recurrence of the last pivot still to be applied
+	// steepest edge: how many of {y, row_q, v} fit in the staging area (fuse: at least y does)
+	const int nstage = SE && fuse ? (int)((long long)DYN_SMEM_BYTES / (d.ld * (long long)sizeof(T)) < 3 ? (long long)DYN_SMEM_BYTES / (d.ld * (long long)sizeof(T)) : 3) : 0;
 
 	const long long it0 = it;
 	while (it < it_end) {
 		// ---- pricing + entering column (v4:288-302)
 		stamp(d, it - it0, 0);
-		if (fuse) {
+		if (SE) {
+			SeUpd u;
+			u.on = pendg;
+			u.p = p;
+			u.leaving = pendg ? __ldcg(&ctl->leaving) : -1;
+			u.alpha_q = pendg ? __ldcg(&ctl->alpha_q) : 1.0;
+			T gp = T(0);
+			if (fuse) {
+				sy_keep = book2_prologue<T, true>(d, sh, ysm, pend2, p, q, me, G, &gp, nstage);
+				if (pendg && !pend2) { T sx_, sy_; book2_scalars<T, true>(d, sh, p, sx_, sy_, &gp); }
+			} else if (pendg) { T sx_, sy_; book2_scalars<T, true>(d, sh, p, sx_, sy_, &gp); }
+			u.gamma_p = (double)gp;
+			const T* const vec[3] = {fuse ? ysm : d.y, nstage > 1 ? ysm + d.ld : d.row_q, nstage > 2 ? ysm + 2 * d.ld : d.vbt};
+			price_phase_se<T>(d, sh, vec, u, me, G);
+		} else if (fuse) {
 			sy_keep = book2_prologue<T>(d, sh, ysm, pend2, p, q, me, G);
 			price_phase_direct<T>(d, sh, ysm, me, G);
 		} else if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, me, G);
@@ -1131,8 +1302,14 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 		stamp(d, it - it0, 1);
 		if (me == 0 && threadIdx.x == 0) ctl->abort_latched = *(volatile int*)&ctl->abort_req;   // before CTA 0 arrives: one value for all
 		grid_barrier(ctl, epoch, G);
-		if (me == 0 && threadIdx.x == 0) ctl->price_ctr = 0;     // every CTA is past pricing; next use is barriers away
+		if (me == 0 && threadIdx.x == 0) { ctl->price_ctr = 0; if (SE) ctl->btran_ctr = 0; }   // every CTA is past pricing; next use is barriers away
 		reduce_cands(d.cand, G, min_e, p, sh);
+		if (SE) {                                                 // optimality from min e (v4:299), the pivot from the weighted candidate
+			double sc; long long pse;
+			reduce_cands(d.cand2, G, sc, pse, sh);
+			if (pse != LLONG_MAX) p = pse;
+			pendg = false;                                         // the recurrence has been applied by this pass
+		}
 		if (pend2) { y_flush<T>(d, sy_keep, me, G); pend2 = false; }   // read again two barriers from here at the earliest
 		stamp(d, it - it0, 2);
 		if (__ldcg(&ctl->abort_latched)) { aborted = 1; break; }
@@ -1168,7 +1345,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 		stamp(d, it - it0, 5);
 
 		// ---- pivot (v4:331-356)
-		book1_phase<T>(d, sh, p, q, me, G);
+		book1_phase<T, SE>(d, sh, p, q, me, G);
+		if (SE) { btran_phase<T>(d, sh, d.alpha, me, G); pendg = true; }
 		stamp(d, it - it0, 6);
 		grid_barrier(ctl, epoch, G);
 		stamp(d, it - it0, 7);
@@ -1192,6 +1370,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
 			ctl->status = status; ctl->done = done; ctl->aborted = aborted;
 			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
+			if (SE) ctl->se_pending = pendg ? 1 : 0;
 		}
 	}
 }
@@ -1557,6 +1736,40 @@ __device__ void fetch_column(const Dev<T>& d, long long p, int part, int nparts)
 		*reinterpret_cast<V*>(d.acol + i) = M::ld_nc(src + i);
 }
 
+// X2 producer: alpha of the local rows = sum of the chunk partials (left to right), stored into
+// every rank's alpha; the ratio test of those rows (v4:199-208) gives this CTA's candidate.
+template <typename T>
+__device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, int part, int nparts) {
+	const int tid = threadIdx.x;
+	double best_v = CUDART_INF;
+	long long best_i = LLONG_MAX;
+	long long elig = 0;
+	for (long long il = (long long)part * NT + tid; il < d.ldb; il += (long long)nparts * NT) {
+		const T a = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
+		const long long i = d.row0 + il;
+		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
+		if (i < d.m && a > (T)d.pivot_tol) {
+			++elig;
+			const double th = (double)(d.x_b[i] / a);
+			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+		}
+	}
+	block_argmin(best_v, best_i, sh);
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) elig += __shfl_xor_sync(0xffffffffu, elig, off);
+	__syncthreads();
+	if ((tid & 31) == 0) sh.red_c[tid >> 5] = elig;
+	__syncthreads();
+	if (tid == 0) {
+		long long c = 0;
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) c += sh.red_c[w];
+		d.cand[part].val = best_v;
+		d.cand[part].idx = best_i;
+		d.cnt[part] = c;
+	}
+}
+
 // book1, sharded: E_q and the c_b.E_q slice partials on every rank (replicated data);
 // X3 producer: the owner of row q gathers it from its B^-1 block, forms the row_q.b slice
 // partials and stores both into every rank's mailbox.
@@ -1643,14 +1856,23 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 			if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
 		}
 		stamp(d, it - it0, 3, me);
-		if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
-		else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, dense ? d.acol : nullptr, p - d.ns, pivots & 1, me, G);
+		const T* acol = dense ? d.acol : nullptr;
+		if (d.fuse_ratio) {
+			// (experiment, off by default: the per-tile release of the group counts costs more than it saves)
+			if (pending) update_ftran_phase<T, WC, true, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			else         update_ftran_phase<T, WC, false, true, true>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			stamp(d, it - it0, 4, me);
+			if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, d.rcand, d.ngrp, d.rcnt, 0);
+		} else {
+			if (pending) update_ftran_phase<T, WC, true, true, false>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			else         update_ftran_phase<T, WC, false, true, false>(d, sh, ringbuf, acol, p - d.ns, pivots & 1, me, G);
+			stamp(d, it - it0, 4, me);
+			if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
+			// ---- X2: alpha slices to every rank together with the ratio test of the local rows (v4:311-325)
+			push_alpha_ratio<T>(d, sh, me, G);
+			if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, d.cand, G, d.cnt, 0);
+		}
 		pending = 0;
-		stamp(d, it - it0, 4, me);
-
-		// ---- X2: the row groups have stored their alpha slices into every rank and left their candidates;
-		// the last CTA to arrive publishes the rank's record (v4:311-325)
-		if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, d.rcand, d.ngrp, d.rcnt, 0);
 		double th;
 		long long elig;
 		if (!gather_records(d, mine->rc, xe, sh, th, q, elig)) { bad = 1; break; }
@@ -1790,6 +2012,37 @@ __global__ void __launch_bounds__(NT) k_objective(Dev<T> d) {
 }
 
 // ---------------------------------------------------------------- setup kernels
+
+// steepest-edge reference framework = the slack basis (B^-1 = I): gamma_j = 1 + |a_j|^2 in the pricing order of
+// the dots; unit (slack) columns 2.  One pass over the local A block.
+template <typename T>
+__global__ void __launch_bounds__(NT) k_gamma_init(Dev<T> d) {
+	__shared__ Smem sh;
+	using M = Mem<T>;
+	using V = typename VecT<T>::V;
+	constexpr int VN = VecT<T>::N;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (long long col = blockIdx.x; col < d.nsl; col += gridDim.x) {
+		const T* a = d.A + col * d.ld;
+		T acc[VN];
+#pragma unroll
+		for (int v = 0; v < VN; ++v) acc[v] = T(0);
+		for (long long i = (long long)tid * VN; i < d.ld; i += (long long)NT * VN) {
+			const V av = M::ld_nc(a + i);
+#pragma unroll
+			for (int v = 0; v < VN; ++v) acc[v] = fma_t(M::get(av, v), M::get(av, v), acc[v]);
+		}
+		T s = acc[0];
+#pragma unroll
+		for (int v = 1; v < VN; ++v) s = s + acc[v];
+		s = warp_butterfly_sum(s);
+		__syncthreads();
+		if (lane == 0) sh.wsum[0][0][warp] = (double)s;
+		__syncthreads();
+		if (tid == 0) d.gamma[d.col0 + col] = T(1) + warp_sums<T>(sh, 0, 0);
+	}
+	for (long long k = d.k0 + (long long)blockIdx.x * NT + tid; k < d.k1; k += (long long)gridDim.x * NT) d.gamma[d.ns + k] = T(2);
+}
 
 // slack-basis initial state (v4:272-277): B^-1 = I, c_b = c[n-m..n), x_b = b,
 // b_ixs[j] = n-m+j, y = c_b; padding rows zero.

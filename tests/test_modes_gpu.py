@@ -1,0 +1,88 @@
+"""Modes outside the reference's parity contract: they change the pivot sequence, so the
+checker is the oracle running the SAME rule with the engine's summation order (bit-exact traces), plus the
+mode-independent facts: same optimum as the reference rule, optimality certificate."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(sol, ref, tag):
+    assert int(sol.status) == ref.status and sol.pivots == ref.pivots and sol.iterations == ref.iterations, \
+        (tag, sol.status, sol.pivots, ref.status, ref.pivots)
+    assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist(), tag
+    assert np.array_equal(sol.x_b, ref.x_b) and np.array_equal(sol.b_ixs, ref.b_ixs) and sol.z == ref.z, tag
+
+
+@pytest.mark.parametrize("m,n,seed,dtype,eps", [
+    (64, 128, 1, np.float64, 1e-9), (192, 448, 1, np.float64, 1e-9), (300, 700, 2, np.float64, 1e-9),
+    (77, 300, 5, np.float64, 1e-9), (1024, 2048, 1, np.float64, 1e-9), (2048, 4096, 1, np.float64, 1e-9),
+    (200, 520, 3, np.float32, 1e-4)])
+def test_steepest_edge_bit_exact_against_oracle(oracle, engine_lib, m, n, seed, dtype, eps):
+    """pricing_rule = 1 (README.md:16-17 'steepest edge with a recurrence'): same pivots, x_b, b_ixs and z as the
+    oracle's steepest edge in the engine's summation order; same optimum as Dantzig; far fewer pivots."""
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(m, n, seed, dtype=dtype)
+    ref = oracle.solve(A, b, c, eps=eps, max_iter=1 << 20, order=1, pricing_rule=1)
+    sol = lp.solve(A, b, c, eps=eps, max_iter=1 << 20, pricing_rule=1)
+    _same(sol, ref, f"steepest edge {m}x{n}")
+    dz = lp.solve(A, b, c, eps=eps, max_iter=1 << 20)
+    assert sol.status == lp.SolveStatus.OptimumFound
+    assert abs(sol.z - dz.z) <= (1e-9 if dtype == np.float64 else 5e-4) * abs(dz.z)
+    if m >= 192:
+        assert sol.pivots < dz.pivots
+
+
+def test_steepest_edge_windows_geometry_and_exact_problems(oracle, engine_lib):
+    """The pending weight recurrence crosses launch boundaries (windows of uneven length), the result does not
+    depend on the grid / fused-prologue choice, and Klee-Minty / assignment stay exact."""
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(640, 1400, 5)
+    m, n = A.shape
+    ref = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20, order=1, pricing_rule=1)
+    for kw in ({}, {"grid_ctas": 3}, {"fuse_book2": -1}, {"grid_ctas": 148, "tile_shape": 2}):
+        with lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 20, pricing_rule=1, **kw) as e:
+            e.upload(A, b, c)
+            r = e.run(5)
+            while r["status"] == lp.SolveStatus.MaxIter:
+                r = e.run(37)
+            x_b, b_ixs, _ = e.download()
+            tr = e.trace()
+            assert r["pivots"] == ref.pivots and r["z"] == ref.z, kw
+            assert tr[:, 0].tolist() == ref.trace_p.tolist() and tr[:, 1].tolist() == ref.trace_q.tolist(), kw
+            assert np.array_equal(x_b, ref.x_b) and np.array_equal(b_ixs, ref.b_ixs), kw
+            e.reset()                                    # weights start over with the slack basis
+            r2 = e.run(1 << 20)
+            assert r2["pivots"] == ref.pivots and r2["z"] == ref.z, kw
+    A, b, c = oracle.gen_klee_minty(12)
+    ref = oracle.solve(A, b, c, eps=1e-4, max_iter=1 << 20, order=1, pricing_rule=1)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20, pricing_rule=1, grid_ctas=2)
+    _same(sol, ref, "klee-minty 12")
+    assert sol.z == 5.0 ** 12
+    A, b, c, w = oracle.gen_assignment(16, 1)
+    ref = oracle.solve(A, b, c, eps=1e-4, max_iter=1 << 20, order=1, pricing_rule=1)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20, pricing_rule=1)
+    _same(sol, ref, "assignment 16")
+
+
+def test_steepest_edge_rejected_where_unsupported(engine_lib):
+    import simplex_method_gpu_b200 as lp
+    from simplex_method_gpu_b200 import capi
+    with pytest.raises(capi.B200LPError):
+        lp.Engine(64, 128, pricing_rule=1, mode=1)
+    with pytest.raises(capi.B200LPError):
+        lp.Engine(64, 128, pricing_rule=1, devices=[0, 0])
+    with pytest.raises(capi.B200LPError):
+        lp.Engine(64, 128, pricing_rule=7)
+
+
+@pytest.mark.parametrize("tol", [1e-9, 1e-3])
+def test_pivot_tol_matches_oracle(oracle, engine_lib, tol):
+    """pivot_tol: eligibility alpha > pivot_tol (v4:203 is the strict alpha > 0 = default)."""
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(256, 600, 4)
+    ref = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20, order=1, pivot_tol=tol)
+    sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20, pivot_tol=tol)
+    _same(sol, ref, f"pivot_tol {tol}")
+    multi = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20, pivot_tol=tol, devices=[0, 0])
+    _same(multi, ref, f"pivot_tol {tol} multi")

@@ -118,3 +118,24 @@ def test_golden_traces(oracle):
         assert s.trace_p[:len(g["p_head"])].tolist() == g["p_head"], name
         assert s.trace_q[:len(g["q_head"])].tolist() == g["q_head"], name
         assert abs(s.z - g["z"]) <= 1e-12 * max(1.0, abs(g["z"])), name
+
+
+@pytest.mark.parametrize("kw", [dict(pricing_rule=1), dict(ratio_mode=1), dict(ratio_mode=2, harris_delta=1e-9),
+                                dict(pivot_tol=1e-9), dict(pricing_rule=1, ratio_mode=2, harris_delta=1e-9)])
+def test_optional_modes_reach_the_reference_optimum(oracle, kw):
+    """Modes outside the parity contract (simplex_oracle.h): a different pivot sequence, the same optimum as the
+    reference's rule and as HiGHS; steepest edge needs far fewer pivots; both summation orders agree on the optimum."""
+    from scipy.optimize import linprog
+    m = 256
+    A, b, c = oracle.gen_dense(m, 2 * m, 1)
+    base = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    hi = linprog(-c[:m], A_ub=A[:, :m], b_ub=b, method="highs-ds")
+    for order in (0, 1):
+        s = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20, order=order, **kw)
+        assert s.status == oracle.OPTIMUM
+        assert abs(s.z - base.z) <= 1e-9 * abs(base.z) and abs(s.z + hi.fun) <= 1e-9 * abs(hi.fun)
+        if kw.get("pricing_rule") == 1:
+            assert s.pivots < base.pivots // 2
+    km = oracle.gen_klee_minty(10)
+    s = oracle.solve(*km, eps=1e-4, max_iter=1 << 20, **kw)
+    assert s.status == oracle.OPTIMUM and s.z == 5.0 ** 10
