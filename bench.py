@@ -100,11 +100,12 @@ def profiled_traffic(workload, pivots_per_launch):
         return None, None
 
 
-def time_to_optimal(name, wl, dev=0):
-    """Whole solve from the slack basis to the optimum on one GPU (the other half of BASELINE.json's metric)."""
+def time_to_optimal(name, wl, dev=0, rule=0):
+    """Whole solve from the slack basis to the optimum on one GPU (the other half of BASELINE.json's metric).
+    rule 0 = the reference's Dantzig rule (v4:288-302), 1 = steepest edge (options.pricing_rule, README.md:16-17)."""
     import simplex_method_gpu_b200 as lp
     m, n = wl["m"], wl["n"]
-    eng = lp.Engine(m, n, np.float64, eps=EPS, max_iter=1 << 40, device=dev)
+    eng = lp.Engine(m, n, np.float64, eps=EPS, max_iter=1 << 40, device=dev, pricing_rule=rule)
     eng.generate_dense(SEED)
     eng.run(8)                       # warm-up launch
     eng.reset()
@@ -113,8 +114,13 @@ def time_to_optimal(name, wl, dev=0):
     wall = time.perf_counter() - t0
     x_b, b_ixs, y = eng.download()
     drift, scale = eng.check_basis()          # |B^-1 b - x_b| after all those rank-1 updates without a refactorisation
+    bytes_pp = eng.bytes_per_pivot
     eng.close()
-    out = {"workload": f"{name}: dense LP m={m} n={n}, seed {SEED}, slack basis to optimum", "status": int(r["status"]),
+    bpp = bytes_pp
+    out = {"workload": f"{name}: dense LP m={m} n={n}, seed {SEED}, slack basis to optimum",
+           "pricing_rule": "steepest edge (Goldfarb-Reid recurrence)" if rule else "Dantzig (the reference's rule)",
+           "status": int(r["status"]), "bytes_per_pivot": bpp,
+           "achieved_GBps": bpp * r["pivots"] / (r["ms_solve"] * 1e-3) / 1e9,
            "basis_drift": {"max_abs_Binv_b_minus_x_b": drift, "max_abs_x_b": scale},
            "pivots": int(r["pivots"]), "iterations": int(r["iterations"]), "z": r["z"],
            "seconds": r["ms_solve"] * 1e-3, "wall_seconds": wall, "pivots_per_s": r["pivots"] / (r["ms_solve"] * 1e-3)}
@@ -491,6 +497,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", default="C2,C3", help="comma list of extra single-GPU workloads reported under 'extra' (both arms)")
     ap.add_argument("--tto", default="C2,C3", help="comma list of workloads solved to optimality (time-to-optimal), '' = none")
+    ap.add_argument("--tto-se", default="C2,C3,C4", help="workloads solved to optimality with steepest-edge pricing "
+                                                         "(options.pricing_rule = 1; a different pivot sequence, same optimum)")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU port")
     ap.add_argument("--ref-pivots", type=int, default=0)
     args = ap.parse_args()
@@ -521,11 +529,16 @@ def main():
             r = run_b200_single(sub, WORKLOADS[name])
             extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "roofline", "config", "device_loop", "clocks",
                                              "gpu_launches", "trace_sha256", "z_after_window", "trace_matches_golden") if k in r}
-        tto = {}
+        tto, tto_se = {}, {}
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
         for name in [x for x in args.tto.split(",") if x]:
-            tto[name] = time_to_optimal(name, WORKLOADS[name], int(os.environ.get("LOCAL_RANK", "0")))
+            tto[name] = time_to_optimal(name, WORKLOADS[name], dev)
+        for name in [x for x in args.tto_se.split(",") if x]:
+            tto_se[name] = time_to_optimal(name, WORKLOADS[name], dev, rule=1)
         if tto:
             extra["time_to_optimal"] = tto
+        if tto_se:
+            extra["time_to_optimal_steepest_edge"] = tto_se
         if extra:
             out["extra"] = extra
     if rank == 0 and out is not None:

@@ -77,7 +77,14 @@ typedef struct {
 	int32_t pricing_rule; /* 0 = Dantzig, the reference's rule (v4:288-302); 1 = steepest edge with the Goldfarb-Reid
 	                         recurrence (the reference's to-do list, README.md:16-17): a different pivot sequence, far
 	                         fewer pivots, one more read of B^-1 per pivot; single GPU, persistent kernel */
-	int32_t reserved[2];
+	int32_t ratio_mode;   /* ratio test (the reference's open items, README.md:29-30): 0 = textbook, the reference's
+	                         (v4:199-208); 1 = bounded: theta = max(x_b, 0) / alpha, a slightly negative x_b never
+	                         yields a negative step; 2 = Harris two-pass: theta_max = min (max(x_b,0) + harris_delta) / alpha,
+	                         then the LARGEST alpha among the rows with max(x_b,0)/alpha <= theta_max (one more O(m) pass
+	                         and grid barrier; single GPU).  Mirrored by the oracle (oracle_opts). */
+	int32_t resident;     /* mid-size LPs (m ~ 128 ... 1500): keep A and B^-1 in the shared memory of the whole grid
+	                         (simplex_resident): 0 = auto (when they fit), -1 = never */
+	double  harris_delta; /* ratio_mode 2: feasibility tolerance of the first pass (e.g. 1e-9) */
 } b200lp_options;
 
 typedef struct {
@@ -207,6 +214,18 @@ int b200lp_upload_columns(b200lp_engine* e, const void* Acols, int64_t col0, int
  * runs (it overwrites alpha).  Changes nothing the loop reads afterwards.  On a sharded engine (one rank of a
  * multi-process run) the maxima are over the rank's own rows; b200lp_create_multi engines return the global ones. */
 int b200lp_check_basis(b200lp_engine* e, double* xb_err, double* xb_scale);
+
+/* Refactorisation: rebuild B^-1 from the current basis alone (identity + one replayed pivot per non-slack basis
+ * position, the loop's own update + FTRAN kernel), then x_b = B^-1 b and y = c_b^T B^-1 from the fresh inverse.
+ * The reference never does this (README.md:29-30 lists the numerical guards as open); nothing in the parity runs
+ * calls it.  rel_pivot_tol: a replay pivot needs |alpha_q| >= rel_pivot_tol * max|alpha| (<= 0: 1e-9); positions that
+ * do not qualify yet are retried later.  replayed (optional) receives the number of replayed pivots.  Single GPU.
+ * After it the basis (b_ixs, c_b) is unchanged, the pivot counters too. */
+int b200lp_refactor(b200lp_engine* e, double rel_pivot_tol, int64_t* replayed);
+/* b200lp_run in windows of `window` iterations with b200lp_check_basis after each one and b200lp_refactor whenever
+ * the drift exceeds drift_tol * max|x_b|.  refactorisations (optional) counts them. */
+int b200lp_run_guarded(b200lp_engine* e, int64_t iterations, int64_t window, double drift_tol, b200lp_result* res,
+		int64_t* refactorisations);
 
 /* ---- in-kernel phase profile (options.profile > 0) ----
  * CTA 0 of the persistent kernel stamps %globaltimer (ns) at every phase boundary; one record of

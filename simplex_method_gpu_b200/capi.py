@@ -24,6 +24,7 @@ EXPORTS = [
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
     "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile", "b200lp_check_basis",
     "b200lp_solve_f64_multi", "b200lp_solve_f32_multi", "b200lp_create_multi", "b200lp_abort",
+    "b200lp_refactor", "b200lp_run_guarded",
     # include/b200lp_io.h
     "b200lp_read_lp", "b200lp_write_lp_text", "b200lp_write_lp_binary", "b200lp_free_problem",
 ]
@@ -35,7 +36,8 @@ class Options(C.Structure):
                 ("price_cols", C.c_int32), ("l2_persist_mb", C.c_int32),
                 ("price_mode", C.c_int32), ("ratio_group_rows", C.c_int32), ("pivot_tol", C.c_double),
                 ("price_tail", C.c_int32), ("fuse_book2", C.c_int32), ("fuse_ratio", C.c_int32),
-                ("pricing_rule", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("pricing_rule", C.c_int32), ("ratio_mode", C.c_int32), ("resident", C.c_int32),
+                ("harris_delta", C.c_double)]
 
 
 class Result(C.Structure):
@@ -77,6 +79,8 @@ def lib() -> C.CDLL:
         "b200lp_solve_f32_multi": (C.c_int, [vp, vp, vp, i64, i64, PO, C.POINTER(i32), i32, vp, vp, vp, i64, PR]),
         "b200lp_create_multi": (C.c_int, [i32, i64, i64, C.POINTER(i32), i32, PO, C.POINTER(vp)]),
         "b200lp_abort": (C.c_int, [vp]),
+        "b200lp_refactor": (C.c_int, [vp, dbl, C.POINTER(i64)]),
+        "b200lp_run_guarded": (C.c_int, [vp, i64, i64, dbl, PR, C.POINTER(i64)]),
         "b200lp_set_memory_cache": (C.c_int, [i32]),
         "b200lp_create": (C.c_int, [i32, i64, i64, PO, C.POINTER(vp)]),
         "b200lp_destroy": (C.c_int, [vp]),

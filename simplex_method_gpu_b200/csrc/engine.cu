@@ -62,6 +62,7 @@ struct b200lp_engine {
 	virtual int download_profile(uint64_t* out, int64_t cap_iters, int64_t* n_iters) = 0;
 	virtual int check_basis(double* xb_err, double* xb_scale) = 0;
 	virtual int abort() = 0;
+	virtual int refactor(double rel_pivot_tol, int64_t* replayed) = 0;
 	cudaStream_t stream = nullptr;
 	int rank = 0, nranks = 1;
 	int grid = 0;
@@ -196,7 +197,7 @@ public:
 		else g = num_sms * std::min(occ, 4);
 		grid = std::max(1, std::min(g, max_grid));
 		CU(alloc(&d.cand, (size_t)max_grid + 2));
-		CU(alloc(&d.cand2, (size_t)max_grid + 2));
+		CU(alloc(&d.cand2, (size_t)2 * (max_grid + 2)));
 		CU(alloc(&d.cnt, (size_t)max_grid + 2));
 
 		// tile shape of the update+FTRAN pass: tiles are handed out dynamically, so the tallest row
@@ -222,8 +223,13 @@ public:
 			CU(cudaMemsetAsync(d.grp_done, 0, ((size_t)d.ngrp + 1) * sizeof(unsigned int), stream));
 		}
 		d.pivot_tol = sizeof(T) == 4 ? (double)(float)opt.pivot_tol : opt.pivot_tol;
+		d.ratio_mode = opt.ratio_mode;
+		d.harris_delta = sizeof(T) == 4 ? (double)(float)opt.harris_delta : opt.harris_delta;
+		if (opt.ratio_mode < 0 || opt.ratio_mode > 2) return fail(B200LP_ERR_ARG, "ratio_mode must be 0, 1 or 2");
+		if (opt.ratio_mode == 2 && (nranks > 1 || opt.mode != 0 || opt.fuse_ratio > 0))
+			return fail(B200LP_ERR_ARG, "the Harris ratio test (ratio_mode = 2) needs the single-GPU persistent kernel with the ratio test as its own phase");
 		d.fuse_ratio = opt.fuse_ratio > 0 ? 1 : 0;    // measured: the per-tile release costs more than the phase it saves
-		d.dbg = opt.reserved[0];
+		d.dbg = 0;
 		return B200LP_OK;
 	}
 
@@ -365,6 +371,7 @@ public:
 		}
 		if (opt.mode == 1 && nranks == 1) { int rc = run_phases(iters); return rc ? rc : 1; }
 		if (tiny_ok()) { int rc = run_tiny(iters); return rc ? rc : 1; }
+		if (resident_ok()) { int rc = run_resident(iters); return rc ? rc : 1; }
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
 		if (d.prof_cap > 0) CU(cudaMemsetAsync(d.prof, 0, (size_t)d.prof_cap * NSTAMP * sizeof(unsigned long long), stream));
@@ -509,6 +516,76 @@ public:
 		}
 		if (xb_err) *xb_err = err;
 		if (xb_scale) *xb_scale = scale;
+		return B200LP_OK;
+	}
+
+	// Refactorisation (the reference lists it as open, README.md:29-30; it never rebuilds its product-form inverse):
+	// B^-1 is rebuilt from the basis alone.  Start from the identity (the slack basis) and replay one pivot per basis
+	// position whose column is not that position's slack: FTRAN of the column through the inverse built so far,
+	// pivot on the position's own row, rank-1 update fused into the next FTRAN pass — the same kernels as the loop,
+	// m' <= m passes over B^-1.  A position whose pivot element is too small for now (|alpha_q| < rel_pivot_tol * max|alpha|)
+	// goes to the back of the queue.  Then x_b = B^-1 b and y = c_b^T B^-1 are recomputed from the fresh inverse, so
+	// the drift of the linear updates (v4:347-356) is gone as well.  Single GPU.
+	int refactor(double rel_pivot_tol, int64_t* replayed) override {
+		if (!have_data) return fail(B200LP_ERR_STATE, "refactor before upload/generate");
+		if (nranks > 1) return fail(B200LP_ERR_STATE, "refactor is single-GPU only");
+		CU(cudaSetDevice(opt.device));
+		if (int rc = settle()) return rc;
+		const long long m = d.m;
+		std::vector<int> bix((size_t)m);
+		CU(cudaMemcpy(bix.data(), d.b_ixs, m * sizeof(int), cudaMemcpyDeviceToHost));
+		k_identity<T><<<num_sms * 8, 256, 0, stream>>>(d);
+		launches++;
+		hc.pending = 0;
+		std::vector<long long> queue;
+		for (long long i = 0; i < m; ++i)
+			if (bix[(size_t)i] != (int)(d.ns + i) || d.ns == d.n) queue.push_back(i);   // (slack block not recognised: every position is replayed)
+		std::vector<T> al((size_t)m);
+		int64_t done = 0;
+		size_t stalled = 0;
+		const double tol = rel_pivot_tol > 0 ? rel_pivot_tol : 1e-9;
+		while (!queue.empty()) {
+			const long long q = queue.front();
+			queue.erase(queue.begin());
+			const long long p = bix[(size_t)q];
+			launch_update_ftran(hc.pending != 0, true, p);
+			hc.pending = 0;
+			k_sum_partials<T><<<num_sms, NT, 0, stream>>>(d, d.alpha);
+			launches++;
+			CU(cudaMemcpyAsync(al.data(), d.alpha, m * sizeof(T), cudaMemcpyDeviceToHost, stream));
+			CU(cudaStreamSynchronize(stream));
+			double amax = 0;
+			for (long long i = 0; i < m; ++i) amax = std::max(amax, std::fabs((double)al[(size_t)i]));
+			if (!(std::fabs((double)al[(size_t)q]) >= tol * amax) || amax == 0) {
+				queue.push_back(q);                      // not now: the rows this column needs are not in place yet
+				if (++stalled > queue.size()) return fail(B200LP_ERR_STATE, "refactor: no admissible pivot order (basis singular to working precision); reset the engine");
+				continue;
+			}
+			stalled = 0;
+			k_book1<T><<<grid, NT, 0, stream>>>(d, p, q);   // row_q, E_q of this replay pivot (its dot partials are not used)
+			launches++;
+			hc.pending = 1;
+			++done;
+		}
+		if (hc.pending) { launch_update_ftran(true, false, 0); hc.pending = 0; }
+		CU(cudaGetLastError());
+		// x_b = B^-1 b, y = c_b^T B^-1
+		CU(zero_tickets());
+		const long long tr = (long long)(NWARP / wc) * 32 * VecT<T>::N;
+		const long long tiles = (d.ldb + tr - 1) / tr * d.nchunk;
+		const int g = (int)std::max<long long>(1, std::min<long long>(tiles, grid));
+		if (wc == 1) k_ftran_vec<T, 1><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else if (wc == 2) k_ftran_vec<T, 2><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else if (wc == 4) k_ftran_vec<T, 4><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		else k_ftran_vec<T, 8><<<g, NT, UF_SMEM_BYTES, stream>>>(d, d.b);
+		k_sum_partials<T><<<num_sms, NT, 0, stream>>>(d, d.x_b);
+		k_btran_vec<T><<<num_sms * 2, NT, 0, stream>>>(d, d.c_b, d.acol);
+		k_copy<T><<<num_sms, 256, 0, stream>>>(d.y, d.acol, m);
+		launches += 4;
+		CU(cudaGetLastError());
+		hc.se_pending = hc.se_pending;    // (steepest-edge weights depend on the basis only: untouched)
+		CU(push_ctl());
+		if (replayed) *replayed = done;
 		return B200LP_OK;
 	}
 
@@ -809,9 +886,35 @@ private:
 	// tiny LPs (one warp-wide vector row, everything fits in shared memory): the shared-memory-resident kernel.
 	// Only with the automatic grid: an explicit grid_ctas asks for the general kernel.
 	bool tiny_ok() const {
-		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0 || opt.pricing_rule != 0) return false;
+		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0 || opt.pricing_rule != 0 || opt.ratio_mode == 2) return false;
 		if (d.ld != 32 * VecT<T>::N) return false;
 		return TinyLayout<T>(d.m, d.n, d.ns).bytes(d.m) <= (size_t)200 * 1024;
+	}
+
+	// mid-size LPs whose A and B^-1 fit in the shared memory of the whole grid (one CTA per SM): the resident kernel.
+	// Only with the automatic configuration (an explicit grid, tile shape or pricing path asks for the general kernel).
+	bool resident_ok() const {
+		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0 || opt.pricing_rule != 0 || opt.ratio_mode == 2 ||
+				opt.tile_shape != 0 || opt.price_mode != 0 || opt.fuse_ratio > 0 || opt.resident < 0)
+			return false;
+		if (d.m < 128) return false;                     // a handful of CTAs: the general kernel on a small grid is as good
+		const ResLayout<T> L(d.m, d.ld, d.ns, num_sms);
+		return L.bytes() <= (size_t)200 * 1024 && L.G <= num_sms && L.G <= max_grid;
+	}
+
+	int run_resident(int64_t iters) {
+		hc.it_end = hc.iter + iters;
+		CU(push_ctl());
+		d.res_maxG = num_sms;
+		const ResLayout<T> L(d.m, d.ld, d.ns, num_sms);
+		const size_t smem = L.bytes();
+		CU(cudaFuncSetAttribute(simplex_resident<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CU(cudaEventRecord(ev0, stream));
+		void* args[] = {&d};
+		CU(cudaLaunchCooperativeKernel((const void*)simplex_resident<T>, dim3((unsigned)L.G), dim3(NT), args, smem, stream));
+		launches++;
+		CU(cudaEventRecord(ev1, stream));
+		return B200LP_OK;
 	}
 
 	int run_tiny(int64_t iters) {
@@ -1054,6 +1157,7 @@ public:
 		if (xb_scale) *xb_scale = scale;
 		return B200LP_OK;
 	}
+	int refactor(double, int64_t*) override { return only_single("refactor"); }
 	int phase_price(int64_t*, double*) override { return only_single("phase_price"); }
 	int phase_update_ftran(int64_t) override { return only_single("phase_update_ftran"); }
 	int phase_ratio(int64_t*, int64_t*) override { return only_single("phase_ratio"); }
@@ -1427,6 +1531,39 @@ int b200lp_run(b200lp_engine* e, int64_t iterations, b200lp_result* res) {
 int b200lp_run_async(b200lp_engine* e, int64_t iterations) { NEED(e); return e->run_async(iterations); }
 int b200lp_wait(b200lp_engine* e, b200lp_result* res) { NEED(e); return e->wait(res); }
 int b200lp_abort(b200lp_engine* e) { NEED(e); return e->abort(); }
+int b200lp_refactor(b200lp_engine* e, double rel_pivot_tol, int64_t* replayed) { NEED(e); return e->refactor(rel_pivot_tol, replayed); }
+
+// run() in windows with a drift check after each; refactorise when |B^-1 b - x_b| exceeds drift_tol * max|x_b|
+int b200lp_run_guarded(b200lp_engine* e, int64_t iterations, int64_t window, double drift_tol, b200lp_result* res,
+		int64_t* refactorisations) {
+	NEED(e);
+	if (window <= 0) return fail(B200LP_ERR_ARG, "window must be positive");
+	int64_t left = iterations, nref = 0;
+	b200lp_result r, first;
+	std::memset(&r, 0, sizeof(r));
+	double ms = 0;
+	bool have_first = false;
+	while (left > 0) {
+		const int64_t w = std::min(left, window);
+		int rc = e->run_async(w);
+		if (!rc) rc = e->wait(&r);
+		if (rc) return rc;
+		if (!have_first) { first = r; have_first = true; }
+		ms += r.ms_solve;
+		left -= w;
+		if (r.status != B200LP_STATUS_MAX_ITER || r.aborted) break;
+		double err = 0, scale = 0;
+		if ((rc = e->check_basis(&err, &scale))) return rc;
+		if (err > drift_tol * std::max(scale, 1.0)) {
+			if ((rc = e->refactor(0, nullptr))) return rc;
+			++nref;
+		}
+	}
+	r.ms_solve = ms;
+	if (res) *res = r;
+	if (refactorisations) *refactorisations = nref;
+	return B200LP_OK;
+}
 int b200lp_download(b200lp_engine* e, void* x_b, int32_t* b_ixs, void* y) { NEED(e); return e->download(x_b, b_ixs, y); }
 int b200lp_download_binv(b200lp_engine* e, void* Binv) { NEED(e); if (!Binv) return fail(B200LP_ERR_ARG, "Binv is NULL"); return e->download_binv(Binv); }
 int b200lp_download_trace(b200lp_engine* e, int32_t* pq, int64_t cap, int64_t* n_out) { NEED(e); return e->download_trace(pq, cap, n_out); }

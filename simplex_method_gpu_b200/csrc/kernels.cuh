@@ -126,6 +126,9 @@ struct Dev {
 	int fuse_book2;           // 1: the O(m) updates of a pivot ride in the prologue of the next pricing pass (y in shared memory)
 	int price_tail;           // columns at the end of the local block priced one at a time (shorter tail of the pass)
 	double pivot_tol;         // ratio-test eligibility alpha > pivot_tol (0 = the reference's strict test, v4:203)
+	int res_maxG;             // resident kernel: CTAs available (one per SM)
+	int ratio_mode;           // 0 textbook (v4:199-208), 1 bounded (x_b clamped at 0), 2 Harris two-pass
+	double harris_delta;      // Harris: feasibility tolerance of the first pass
 	Ctl* ctl;
 	int2* trace;
 	long long trace_cap;
@@ -217,6 +220,10 @@ __device__ __forceinline__ T warp_butterfly_sum(T s) {
 	for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
 	return s;
 }
+
+// numerator of the ratio test: x_b itself (v4:205), or clamped at zero in the bounded / Harris modes
+template <typename T>
+__device__ __forceinline__ T ratio_num(T xb, int mode) { return mode >= 1 && xb < T(0) ? T(0) : xb; }
 
 // lexicographic (value, index): the lowest index wins ties, like cub ArgMin (v4:294, 324)
 __device__ __forceinline__ bool cand_better(double v, long long i, double bv, long long bi) {
@@ -828,7 +835,7 @@ __device__ void finish_row_group(const Dev<T>& d, Smem& sh, long long g, long lo
 		for (int k = 0; k < d.nranks; ++k) xalpha(d, k)[i] = a;
 		if (i < d.m && a > tol) {
 			++elig;
-			const double th = (double)(d.x_b[i] / a);
+			const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
 	}
@@ -1067,7 +1074,9 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 		}
 		if (a > (T)d.pivot_tol) {
 			++elig;
-			const double th = (double)(d.x_b[i] / a);
+			const T xb = ratio_num(d.x_b[i], d.ratio_mode);
+			// Harris, first pass: the widest step the tolerance allows (the row is chosen by harris_phase2)
+			const double th = d.ratio_mode == 2 ? (double)((xb + (T)d.harris_delta) / a) : (double)(xb / a);
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
 	}
@@ -1086,6 +1095,24 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
 		d.cand[part].idx = best_i;
 		d.cnt[part] = c;
 	}
+}
+
+// Harris ratio test, second pass: among the eligible rows whose step max(x_b,0)/alpha does not exceed theta_max,
+// the one with the LARGEST pivot element alpha (lowest index on ties) -> cand2[part] as (-alpha, index)
+template <typename T>
+__device__ void harris_phase2(const Dev<T>& d, Smem& sh, double theta_max, int part, int nparts) {
+	const int tid = threadIdx.x;
+	double best_v = CUDART_INF;
+	long long best_i = LLONG_MAX;
+	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
+		const T a = d.alpha[i];
+		if (a > (T)d.pivot_tol && (double)(ratio_num(d.x_b[i], 2) / a) <= theta_max && cand_better(-(double)a, i, best_v, best_i)) {
+			best_v = -(double)a;
+			best_i = i;
+		}
+	}
+	block_argmin(best_v, best_i, sh);
+	if (tid == 0) { d.cand2[part].val = best_v; d.cand2[part].idx = best_i; }
 }
 
 // ---------------------------------------------------------------- phase: bookkeeping 1
@@ -1339,6 +1366,12 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 			stamp(d, it - it0, 4);
 			reduce_cands(d.cand, G, th, q, sh);
 			elig = reduce_counts(d.cnt, G, sh);
+			if (d.ratio_mode == 2 && elig > 0) {        // Harris: th is theta_max, now pick the largest pivot inside it
+				harris_phase2<T>(d, sh, th, me, G);
+				grid_barrier(ctl, epoch, G);
+				double na;
+				reduce_cands(d.cand2, G, na, q, sh);
+			}
 		}
 		pending = 0;
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
@@ -1516,7 +1549,7 @@ __global__ void __launch_bounds__(NT, 1) simplex_tiny(Dev<T> d) {
 			const T a = sal[i];
 			if (a > (T)d.pivot_tol) {
 				++elig;
-				const double th = (double)(sx[i] / a);
+				const double th = (double)(ratio_num(sx[i], d.ratio_mode) / a);
 				if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 			}
 		}
@@ -1590,6 +1623,281 @@ __global__ void __launch_bounds__(NT, 1) simplex_tiny(Dev<T> d) {
 		ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
 		ctl->status = status; ctl->done = done;
 		ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = (double)z; ctl->c_b_q = sh.bc_v;
+	}
+}
+
+// ---------------------------------------------------------------- mid-size LPs: B^-1 and A resident in shared memory
+//
+// m ~ 256 ... 1500 (BASELINE config 2: m = 1024): A and B^-1 fit in the 126 MB L2, but a pivot of the general
+// kernel is ~20 us of tile / barrier latency for ~3 us of L2 streaming (64 tiles for 148 SMs, ~20 dependent L2
+// round trips).  Here the whole LP lives in the shared memory of the grid: CTA c owns rpc consecutive ROWS of B^-1
+// (row-major, every 32-column sub-block padded to 33 so that the per-(row, sub-block) fma chains of a warp hit
+// different banks) and cpc consecutive COLUMNS of A, plus private copies of y, b and the pivot row.  A pivot is
+//   pricing of the own columns (shared memory)                              | B1 -> p
+//   entering column from global A (L2), rank-1 update + FTRAN + ratio test
+//   on the own rows (shared memory)                                         | B2 -> q, alpha_q
+//   E_q of the own rows, products c_b E_q, owner: row q -> global (8 KB)     | B3
+//   every CTA: row_q.b, c_b.E_q, y (own full copy), x_b / c_b / b_ixs (own rows)
+// i.e. three grid barriers and three small L2 exchanges; no matrix byte leaves shared memory inside the loop.
+// Every sum is associated exactly as in the general kernel (file header), so the results are bit-identical to it
+// and to the oracle's order = 1.  State is read from and written back to the same global buffers (same deferred
+// rank-1 update semantics), so windows, downloads, check_basis and the phase entry points see no difference.
+
+template <typename T>
+struct ResLayout {
+	static constexpr int SBP = SUBW + 1;     // padded sub-block
+	long long rpc, cpc, nsb, G;              // rows / columns per CTA, sub-blocks per row, CTAs in use
+	long long Bs, As, y, b, rowq, prod, rowqP, apP, part, xb, cb, al, eq, end;   // element offsets (T)
+	__host__ __device__ static long long r4(long long x) { return (x + 3) / 4 * 4; }
+	__host__ __device__ ResLayout(long long m, long long ld, long long ns, long long maxG) {
+		rpc = (m + maxG - 1) / maxG;
+		G = (m + rpc - 1) / rpc;
+		cpc = (ns + G - 1) / G;
+		nsb = (m + SUBW - 1) / SUBW;
+		long long o = 0;
+		As = o; o += r4(cpc * ld);
+		y = o; o += ld; b = o; o += ld; rowq = o; o += ld; prod = o; o += ld;
+		rowqP = o; o += r4(nsb * SBP); apP = o; o += r4(nsb * SBP);     // row_q / a_p in the padded sub-block layout of Bs
+		Bs = o; o += r4(rpc * nsb * SBP);
+		part = o; o += r4(rpc * nsb);
+		xb = o; o += r4(rpc); cb = o; o += r4(rpc); al = o; o += r4(rpc); eq = o; o += r4(rpc);
+		end = o;
+	}
+	__host__ __device__ size_t bytes() const { return (size_t)end * sizeof(T) + (size_t)r4(rpc) * sizeof(int) + 16; }
+};
+
+// sum of a vector of m values held in shared memory in the order of the O(m) dots (256-element slices: thread t
+// owns element t, warp butterfly, 8 warp sums left to right; slices left to right); PROD: the elements are
+// x[i] * y[i] formed by one fma each, otherwise x[i] as they are.  Result in every thread.
+template <typename T, bool PROD>
+__device__ __forceinline__ T res_sliced_sum(const T* x, const T* y, long long m, Smem& sh) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	T tot = T(0);
+	for (long long s0 = 0; s0 < m; s0 += SLICE) {
+		const long long i = s0 + tid;
+		T t = T(0);
+		if (i < m) t = PROD ? fma_t(x[i], y[i], T(0)) : x[i];
+		t = warp_butterfly_sum(t);
+		__syncthreads();
+		if (lane == 0) sh.dsum[0][warp] = (double)t;
+		__syncthreads();
+		T a = T(0);
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[0][w];
+		tot = tot + a;
+	}
+	return tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
+	using V = typename VecT<T>::V;
+	using M = Mem<T>;
+	constexpr int VN = VecT<T>::N;
+	constexpr int SBP = ResLayout<T>::SBP;
+	__shared__ Smem sh;
+	extern __shared__ __align__(128) unsigned char dynraw[];
+	T* S = reinterpret_cast<T*>(dynraw);
+	const ResLayout<T> L(d.m, d.ld, d.ns, d.res_maxG);
+	T *sA = S + L.As, *sy = S + L.y, *sb = S + L.b, *srq = S + L.rowq, *srqP = S + L.rowqP, *sapP = S + L.apP, *sprod = S + L.prod, *sB = S + L.Bs,
+	  *spart = S + L.part, *sxb = S + L.xb, *scb = S + L.cb, *sal = S + L.al, *seq = S + L.eq;
+	int* sbix = reinterpret_cast<int*>(S + L.end);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int G = gridDim.x, me = blockIdx.x;          // G == L.G
+	const long long m = d.m, ld = d.ld, ns = d.ns, nsb = L.nsb;
+	const long long r0 = (long long)me * L.rpc, nr = r0 < m ? (m - r0 < L.rpc ? m - r0 : L.rpc) : 0;   // own rows
+	const long long c0 = (long long)me * L.cpc, nc = c0 < ns ? (ns - c0 < L.cpc ? ns - c0 : L.cpc) : 0; // own columns
+	const long long nunit = d.n - ns, k0 = nunit * me / G, k1 = nunit * (me + 1) / G;                   // own unit columns
+	Ctl* ctl = d.ctl;
+	unsigned long long epoch = 0;
+
+	// ---- state in
+	for (long long e = tid; e < nc * ld; e += NT) sA[e] = d.A[c0 * ld + e];
+	for (long long e = tid; e < nr * m; e += NT) {
+		const long long r = e % nr, j = e / nr;           // consecutive threads: consecutive rows of one column
+		sB[(r * nsb + j / SUBW) * SBP + j % SUBW] = d.B[(r0 + r) + j * d.ldb];
+	}
+	for (long long i = tid; i < ld; i += NT) {
+		sy[i] = d.y[i]; sb[i] = d.b[i]; sprod[i] = T(0);
+		const T rq = d.row_q[i];
+		srq[i] = rq;
+		if (i < m) srqP[(i / SUBW) * SBP + i % SUBW] = rq;
+	}
+	for (long long r = tid; r < nr; r += NT) {
+		sxb[r] = d.x_b[r0 + r]; scb[r] = d.c_b[r0 + r]; sal[r] = d.alpha[r0 + r]; seq[r] = d.E_q[r0 + r]; sbix[r] = d.b_ixs[r0 + r];
+	}
+	long long it = ctl->iter, pivots = ctl->pivots;
+	const long long it_end = ctl->it_end;
+	int pending = ctl->pending;
+	int status = 0, done = 0, aborted = 0;
+	long long p = ctl->p, q = ctl->q;
+	double min_e = ctl->min_e;
+	const T tol = (T)d.pivot_tol;
+	__syncthreads();
+
+	while (it < it_end) {
+		// ---- pricing of the own columns (v4:288-302): the dots of price_phase, operands in shared memory
+		double best_v = CUDART_INF;
+		long long best_i = LLONG_MAX;
+		int buf = 0;
+		for (long long kq = 0; kq < nc; kq += PRICE_NC, buf ^= 1) {
+			T acc[PRICE_NC][VN];
+#pragma unroll
+			for (int k = 0; k < PRICE_NC; ++k)
+#pragma unroll
+				for (int v = 0; v < VN; ++v) acc[k][v] = T(0);
+			for (long long i = (long long)tid * VN; i < ld; i += (long long)NT * VN) {
+				const V yv = *reinterpret_cast<const V*>(sy + i);
+#pragma unroll
+				for (int k = 0; k < PRICE_NC; ++k) {
+					if (kq + k < nc) {
+						const V av = *reinterpret_cast<const V*>(sA + (kq + k) * ld + i);
+#pragma unroll
+						for (int v = 0; v < VN; ++v) acc[k][v] = fma_t(M::get(av, v), M::get(yv, v), acc[k][v]);
+					}
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < PRICE_NC; ++k) {
+				T s = acc[k][0];
+#pragma unroll
+				for (int v = 1; v < VN; ++v) s = s + acc[k][v];
+				s = warp_butterfly_sum(s);
+				if (lane == 0) sh.wsum[buf][k][warp] = (double)s;
+			}
+			__syncthreads();
+			if (tid < PRICE_NC && kq + tid < nc) {
+				const long long j = c0 + kq + tid;
+				const double e = (double)(warp_sums<T>(sh, buf, tid) - d.c[j]);
+				if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
+			}
+		}
+		for (long long k = k0 + tid; k < k1; k += NT) {      // unit (slack) columns
+			const double e = (double)(sy[k] - d.c[ns + k]);
+			if (cand_better(e, ns + k, best_v, best_i)) { best_v = e; best_i = ns + k; }
+		}
+		block_argmin(best_v, best_i, sh);
+		if (tid == 0) { d.cand[me].val = best_v; d.cand[me].idx = best_i; }
+		if (me == 0 && tid == 0) ctl->abort_latched = *(volatile int*)&ctl->abort_req;
+		grid_barrier(ctl, epoch, G);
+		reduce_cands(d.cand, G, min_e, p, sh);
+		if (__ldcg(&ctl->abort_latched)) { aborted = 1; break; }
+		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
+
+		// ---- entering column (L2), then the pending rank-1 update fused with the FTRAN on the own rows (v4:333, 307-308)
+		for (long long j = tid; j < m; j += NT)
+			sapP[(j / SUBW) * SBP + j % SUBW] = p < ns ? __ldcg(d.A + p * ld + j) : (j == p - ns ? T(1) : T(0));
+		__syncthreads();
+		for (long long w = tid; w < nr * nsb; w += NT) {
+			const long long r = w / nsb, sbk = w % nsb;
+			T* bp = sB + w * SBP;
+			const long long jb = sbk * SUBW;
+			const int ncols = (int)(m - jb < SUBW ? m - jb : SUBW);
+			const T er = seq[r];
+			const T *rqp = srqP + sbk * SBP, *app = sapP + sbk * SBP;   // consecutive lanes: stride 33 -> no bank conflicts
+			T acc = T(0);
+			for (int u = 0; u < ncols; ++u) {
+				T x = bp[u];
+				if (pending) { x = fma_t(er, rqp[u], x); bp[u] = x; }
+				acc = fma_t(x, app[u], acc);
+			}
+			spart[w] = acc;
+		}
+		pending = 0;
+		__syncthreads();
+		// alpha of the own rows: pairwise tree over the 8 sub-blocks of a chunk, chunks left to right; ratio test (v4:311-325)
+		double rv = CUDART_INF;
+		long long ri = LLONG_MAX, elig = 0;
+		if (tid < nr) {
+			const T* pr = spart + (long long)tid * nsb;
+			T a = T(0);
+			for (long long c8 = 0; c8 < nsb; c8 += CHUNK / SUBW) {
+				T t8[CHUNK / SUBW];
+#pragma unroll
+				for (int k = 0; k < CHUNK / SUBW; ++k) t8[k] = c8 + k < nsb ? pr[c8 + k] : T(0);
+				const T ck = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+				a = c8 == 0 ? ck : a + ck;
+			}
+			sal[tid] = a;
+			if (a > tol) {
+				elig = 1;
+				rv = (double)(ratio_num(sxb[tid], d.ratio_mode) / a);
+				ri = r0 + tid;
+			}
+		}
+		block_argmin(rv, ri, sh);
+		elig = __syncthreads_count(elig != 0);
+		if (tid == 0) {
+			// (not d.cand: a slow CTA may still be reducing the pricing candidates of this iteration)
+			d.cand2[me].val = rv; d.cand2[me].idx = ri; d.cnt[me] = elig;
+			d.cand2[G + me].val = ri != LLONG_MAX ? (double)sal[ri - r0] : 0.0;      // alpha at this CTA's candidate
+		}
+		grid_barrier(ctl, epoch, G);
+		double th;
+		reduce_cands(d.cand2, G, th, q, sh);
+		const long long el = reduce_counts(d.cnt, G, sh);
+		if (el == 0) { status = 2; done = 1; ++it; break; }
+		const int owner = (int)(q / L.rpc);
+		const T alpha_q = (T)__ldcg(&d.cand2[G + owner].val);
+		const T c_p = d.c[p];
+
+		// ---- E_q of the own rows, products c_b_new E_q; the owner of row q publishes it (v4:331-332, 340, 354)
+		if (tid < nr) {
+			const long long i = r0 + tid;
+			const T eqv = (i != q) ? (-sal[tid] / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			seq[tid] = eqv;
+			T cb = scb[tid];
+			if (i == q) { ctl->c_b_q = (double)cb; cb = c_p; }
+			d.E_q[i] = fma_t(cb, eqv, T(0));                  // (E_q doubles as the exchange buffer of the products; rewritten at exit)
+		}
+		if (me == owner) {
+			const T* brow = sB + (q - r0) * nsb * SBP;
+			for (long long j = tid; j < m; j += NT) d.row_q[j] = brow[(j / SUBW) * SBP + j % SUBW];
+		}
+		grid_barrier(ctl, epoch, G);
+
+		// ---- every CTA: row_q.b, c_b.E_q, y (own full copy); own rows: x_b, c_b, b_ixs (v4:339-356)
+		for (long long j = tid; j < ld; j += NT) {
+			const T rq = j < m ? __ldcg(d.row_q + j) : T(0);
+			srq[j] = rq;
+			if (j < m) srqP[(j / SUBW) * SBP + j % SUBW] = rq;
+			sprod[j] = j < m ? __ldcg(d.E_q + j) : T(0);
+		}
+		__syncthreads();
+		const T sx = res_sliced_sum<T, true>(srq, sb, m, sh);
+		T syv = res_sliced_sum<T, false>(sprod, nullptr, m, sh);
+		syv += c_p - (T)__ldcg(&ctl->c_b_q);
+		for (long long j = tid; j < m; j += NT) sy[j] = fma_t(syv, srq[j], sy[j]);
+		if (tid < nr) {
+			sxb[tid] = fma_t(sx, seq[tid], sxb[tid]);
+			if (r0 + tid == q) { scb[tid] = c_p; sbix[tid] = (int)p; }
+		}
+		if (me == 0 && tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
+		pending = 1;
+		++pivots;
+		++it;
+		__syncthreads();
+		// (the next exchange through d.E_q / d.row_q is two barriers away: no barrier needed here)
+	}
+
+	// ---- state out (every CTA is past its last read of the exchange buffers after this barrier)
+	grid_barrier(ctl, epoch, G);
+	for (long long e = tid; e < nr * m; e += NT) {
+		const long long r = e % nr, j = e / nr;
+		d.B[(r0 + r) + j * d.ldb] = sB[(r * nsb + j / SUBW) * SBP + j % SUBW];
+	}
+	for (long long r = tid; r < nr; r += NT) {
+		d.x_b[r0 + r] = sxb[r]; d.c_b[r0 + r] = scb[r]; d.alpha[r0 + r] = sal[r]; d.E_q[r0 + r] = seq[r]; d.b_ixs[r0 + r] = sbix[r];
+	}
+	if (me == 0) for (long long i = tid; i < m; i += NT) { d.y[i] = sy[i]; d.row_q[i] = srq[i]; }
+	grid_barrier(ctl, epoch, G);
+	if (me == 0) {
+		const double z = objective<T>(d, sh);
+		if (tid == 0) {
+			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
+			ctl->status = status; ctl->done = done; ctl->aborted = aborted;
+			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
+		}
 	}
 }
 
@@ -1750,7 +2058,7 @@ __device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, int part, int nparts
 		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
 		if (i < d.m && a > (T)d.pivot_tol) {
 			++elig;
-			const double th = (double)(d.x_b[i] / a);
+			const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
 	}
@@ -1984,6 +2292,34 @@ template <typename T>
 __global__ void __launch_bounds__(NT) k_sum_partials(Dev<T> d, T* out) {
 	for (long long il = (long long)blockIdx.x * NT + threadIdx.x; il < d.ldb; il += (long long)gridDim.x * NT)
 		out[il] = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
+}
+
+// out[j] = vec . B^-1[:, j] for the m columns of B^-1 (pricing order of the dot): y = c_b^T B^-1 after a refactorisation
+template <typename T>
+__global__ void __launch_bounds__(NT) k_btran_vec(Dev<T> d, const T* vec, T* out) {
+	__shared__ Smem sh;
+	const T* const v3[3] = {vec, nullptr, nullptr};
+	int buf = 0;
+	for (long long col = blockIdx.x; col < d.m; col += gridDim.x, buf ^= 1) {
+		column_dots<T, 1, 16, 1, true>(d.B + col * d.ldb, d.ldb, d.ldb, v3, sh, buf);
+		__syncthreads();
+		if (threadIdx.x == 0) out[col] = warp_sums<T>(sh, buf, 0);
+		__syncthreads();
+	}
+}
+
+// dst[i] = src[i] for i < n (device vectors)
+template <typename T>
+__global__ void k_copy(T* dst, const T* src, long long n) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// B^-1 = I on the local row block (start of a refactorisation; the O(m) vectors stay)
+template <typename T>
+__global__ void k_identity(Dev<T> d) {
+	const long long tot = d.ldb * d.m;
+	for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x)
+		d.B[e] = (d.row0 + e % d.ldb == e / d.ldb) ? T(1) : T(0);
 }
 
 template <typename T>

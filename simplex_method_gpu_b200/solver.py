@@ -180,6 +180,18 @@ class Engine:
         capi.check(self._L.b200lp_wait(self._h, C.byref(res)))
         return self._result(res)
 
+    def refactor(self, rel_pivot_tol: float = 0.0) -> int:
+        """Rebuild B^-1, x_b and y from the current basis (b200lp_refactor); returns the number of replayed pivots."""
+        k = C.c_int64(0)
+        capi.check(self._L.b200lp_refactor(self._h, float(rel_pivot_tol), C.byref(k)))
+        return k.value
+
+    def run_guarded(self, iterations: int, window: int, drift_tol: float):
+        """run() in windows with a drift check and a refactorisation when needed -> (result, refactorisations)."""
+        res, k = capi.Result(), C.c_int64(0)
+        capi.check(self._L.b200lp_run_guarded(self._h, int(iterations), int(window), float(drift_tol), C.byref(res), C.byref(k)))
+        return self._result(res), k.value
+
     def abort(self):
         """Ask a running loop to stop at its next iteration boundary (b200lp_abort); pair with wait()."""
         capi.check(self._L.b200lp_abort(self._h))

@@ -457,3 +457,55 @@ def test_full_size_invariants(lp, oracle, m, n, head, tail):
         assert r2["z"] == z_prev and np.array_equal(e.trace(), trace1)
         x_b2, b_ixs2, _ = e.download()
         assert np.array_equal(x_b2, x_b) and np.array_equal(b_ixs2, b_ixs)
+
+
+@pytest.mark.parametrize("m,n,seed,dtype,eps", [
+    (128, 256, 1, np.float64, 1e-9), (300, 700, 2, np.float64, 1e-9), (160, 1500, 3, np.float64, 1e-9),
+    (777, 1600, 4, np.float64, 1e-9), (1024, 2048, 1, np.float64, 1e-9), (1100, 2150, 5, np.float64, 1e-9),
+    (520, 1200, 6, np.float32, 1e-4), (1024, 2048, 2, np.float32, 1e-4)])
+def test_resident_kernel_bit_identical_to_general(oracle, engine_lib, m, n, seed, dtype, eps):
+    """simplex_resident (A and B^-1 in the shared memory of the grid, m ~ 128..1500) against the general persistent
+    kernel (options.resident = -1) and the engine-order oracle: same pivots, x_b, b_ixs, z, y and B^-1 bit for bit;
+    uneven windows carry the deferred rank-1 update across launches and across the two kernels."""
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(m, n, seed, dtype=dtype)
+    ref = oracle.solve(A, b, c, eps=eps, max_iter=1 << 20, order=1, want_Binv=True)
+    out = {}
+    for tag, kw in (("resident", {}), ("general", {"resident": -1})):
+        with lp.Engine(m, n, dtype, eps=eps, max_iter=1 << 20, **kw) as e:
+            e.upload(A, b, c)
+            r = e.run(3)
+            while r["status"] == lp.SolveStatus.MaxIter:
+                r = e.run(101)
+            out[tag] = (r, e.download(), e.trace(), e.download_binv())
+    (r1, (x1, i1, y1), t1, B1), (r2, (x2, i2, y2), t2, B2) = out["resident"], out["general"]
+    assert r1["pivots"] == r2["pivots"] == ref.pivots and r1["z"] == r2["z"] == ref.z and r1["iterations"] == ref.iterations
+    assert np.array_equal(t1, t2) and t1[:, 0].tolist() == ref.trace_p.tolist() and t1[:, 1].tolist() == ref.trace_q.tolist()
+    assert np.array_equal(x1, x2) and np.array_equal(i1, i2) and np.array_equal(y1, y2) and np.array_equal(B1, B2)
+    assert np.array_equal(x1, ref.x_b) and np.array_equal(i1, ref.b_ixs) and np.array_equal(B1, ref.Binv)
+    # hand-over between the kernels in the middle of a solve: resident windows, then the general kernel finishes
+    with lp.Engine(m, n, dtype, eps=eps, max_iter=1 << 20) as e:
+        e.upload(A, b, c)
+        e.run(min(17, ref.pivots))
+        mid_x, mid_i, _ = e.download()
+        k = e.trace().shape[0]
+        assert e.trace()[:, 0].tolist() == ref.trace_p[:k].tolist()
+        p, _ = e.phase_price()                       # the phase entry points see the resident kernel's state
+        if k < ref.pivots:
+            assert p == ref.trace_p[k]
+
+
+def test_resident_kernel_degenerate_and_unbounded(oracle, engine_lib):
+    import simplex_method_gpu_b200 as lp
+    A, b, c, w = oracle.gen_assignment(64, 1)              # m = 128: ties everywhere
+    ref = oracle.solve(A, b, c, eps=1e-4, max_iter=1 << 20, order=1)
+    sol = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20)
+    gen = lp.solve(A, b, c, eps=1e-4, max_iter=1 << 20, resident=-1)
+    assert sol.trace[:, 0].tolist() == ref.trace_p.tolist() and sol.trace[:, 1].tolist() == ref.trace_q.tolist()
+    assert np.array_equal(sol.trace, gen.trace) and sol.z == gen.z == ref.z and np.array_equal(sol.x_b, gen.x_b)
+    A, b, c = oracle.gen_dense(200, 440, 8)
+    A[:, 5] = -np.abs(A[:, 5])                              # a column with no positive entry and an attractive cost: unbounded
+    c[5] = 1e3
+    ref = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20, order=1)
+    sol = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    assert ref.status == oracle.UNBOUNDED and int(sol.status) == ref.status and sol.pivots == ref.pivots and sol.iterations == ref.iterations

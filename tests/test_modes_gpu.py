@@ -86,3 +86,72 @@ def test_pivot_tol_matches_oracle(oracle, engine_lib, tol):
     _same(sol, ref, f"pivot_tol {tol}")
     multi = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20, pivot_tol=tol, devices=[0, 0])
     _same(multi, ref, f"pivot_tol {tol} multi")
+
+
+@pytest.mark.parametrize("kw", [dict(ratio_mode=1), dict(ratio_mode=2, harris_delta=1e-9), dict(ratio_mode=2, harris_delta=1e-6),
+                                dict(ratio_mode=2, harris_delta=1e-9, pricing_rule=1), dict(ratio_mode=1, pivot_tol=1e-7)])
+def test_ratio_modes_bit_exact_against_oracle(oracle, engine_lib, kw):
+    """The reference's open items (README.md:29-30): bounded ratio test (x_b clamped at 0) and the Harris two-pass
+    test with the largest pivot element; same rule in the oracle with the engine's summation order -> same pivots."""
+    import simplex_method_gpu_b200 as lp
+    for name, (A, b, c), eps in (("dense 300x700", oracle.gen_dense(300, 700, 2), 1e-9),
+                                 ("dense 1024x2048", oracle.gen_dense(1024, 2048, 1), 1e-9),
+                                 ("assignment 16", oracle.gen_assignment(16, 1)[:3], 1e-4),
+                                 ("klee-minty 10", oracle.gen_klee_minty(10), 1e-4)):
+        ref = oracle.solve(A, b, c, eps=eps, max_iter=1 << 20, order=1, **kw)
+        sol = lp.solve(A, b, c, eps=eps, max_iter=1 << 20, **kw)
+        _same(sol, ref, f"{name} {kw}")
+        base = lp.solve(A, b, c, eps=eps, max_iter=1 << 20)
+        if sol.status == lp.SolveStatus.OptimumFound:
+            assert abs(sol.z - base.z) <= 1e-9 * max(1.0, abs(base.z)), (name, kw)
+
+
+def test_harris_rejected_where_unsupported(engine_lib):
+    import simplex_method_gpu_b200 as lp
+    from simplex_method_gpu_b200 import capi
+    for kw in (dict(ratio_mode=2, devices=[0, 0]), dict(ratio_mode=2, mode=1), dict(ratio_mode=3)):
+        with pytest.raises(capi.B200LPError):
+            lp.Engine(64, 128, **kw)
+
+
+def test_refactorisation_rebuilds_the_inverse(oracle, engine_lib):
+    """b200lp_refactor (the reference lists the numerical guards as open, README.md:29-30): B^-1 rebuilt from the
+    basis alone must invert the basis matrix, x_b / y must be B^-1 b / c_b^T B^-1 (checked with numpy, an independent
+    implementation), and the solve continues to the same optimum."""
+    import simplex_method_gpu_b200 as lp
+    for (m, n, seed, k) in ((300, 700, 2, 60), (1024, 2048, 1, 500)):
+        A, b, c = oracle.gen_dense(m, n, seed)
+        full = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+        for kw in ({}, {"pricing_rule": 1}):
+            with lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 20, **kw) as e:
+                e.upload(A, b, c)
+                r = e.run(k)
+                x0, ix0, y0 = e.download()
+                replayed = e.refactor()
+                x1, ix1, y1 = e.download()
+                Binv = e.download_binv()
+                assert np.array_equal(ix0, ix1)
+                assert replayed == int(np.sum(ix1 != np.arange(n - m, n)))
+                B = A[:, ix1]
+                assert np.abs(B @ Binv - np.eye(m)).max() <= 1e-9
+                assert np.abs(x1 - np.linalg.solve(B, b)).max() <= 1e-9 * np.abs(x1).max()
+                assert np.abs(y1 - np.linalg.solve(B.T, c[ix1])).max() <= 1e-9 * max(1.0, np.abs(y1).max())
+                assert np.abs(x1 - x0).max() <= 1e-9 * np.abs(x0).max() and np.abs(y1 - y0).max() <= 1e-9 * max(1.0, np.abs(y0).max())
+                assert e.check_basis()[0] <= 1e-10 * np.abs(x1).max()
+                r = e.run(1 << 20)
+                assert r["status"] == lp.SolveStatus.OptimumFound and abs(r["z"] - full.z) <= 1e-9 * abs(full.z), kw
+
+
+def test_guarded_run_refactorises_on_drift(oracle, engine_lib):
+    import simplex_method_gpu_b200 as lp
+    A, b, c = oracle.gen_dense(512, 1200, 3)
+    full = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20)
+    with lp.Engine(512, 1200, np.float64, eps=1e-9, max_iter=1 << 20) as e:
+        e.upload(A, b, c)
+        r, nref = e.run_guarded(1 << 20, 64, 0.0)        # drift_tol 0: every window triggers a refactorisation
+        assert r["status"] == lp.SolveStatus.OptimumFound and nref >= 1
+        assert abs(r["z"] - full.z) <= 1e-9 * abs(full.z)
+    with lp.Engine(512, 1200, np.float64, eps=1e-9, max_iter=1 << 20) as e:
+        e.upload(A, b, c)
+        r, nref = e.run_guarded(1 << 20, 64, 1e-6)       # a healthy inverse never triggers one
+        assert nref == 0 and r["pivots"] == full.pivots and r["z"] == full.z

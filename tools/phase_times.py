@@ -52,14 +52,14 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     e = ShardedEngine(a.m, a.n, np.float64, rank=rank, world=world, device=local, eps=1e-9, max_iter=1 << 30,
                       profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode,
-                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse, fuse_ratio=a.fuse_ratio, pricing_rule=a.rule, reserved=(C.c_int32 * 2)(a.dbg, 0))
+                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse, fuse_ratio=a.fuse_ratio, pricing_rule=a.rule)
     e.generate_dense(1)
     e.connect()
     dist.barrier()
     names = names["sharded"]
 else:
     e = lp.Engine(a.m, a.n, np.float64, eps=1e-9, max_iter=1 << 30, profile=a.pivots, grid_ctas=a.grid, tile_shape=a.shape, price_cols=a.price_cols, l2_persist_mb=a.l2, price_mode=a.price_mode,
-                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse, fuse_ratio=a.fuse_ratio, pricing_rule=a.rule, reserved=(C.c_int32 * 2)(a.dbg, 0))
+                      ratio_group_rows=a.group_rows, price_tail=a.tail, fuse_book2=a.fuse, fuse_ratio=a.fuse_ratio, pricing_rule=a.rule)
     e.generate_dense(1)
     names = names["single"]
 
