@@ -115,7 +115,8 @@ public:
 		CU(cudaEventCreate(&ev1));
 
 		const size_t ld = (size_t)d.ld, m = (size_t)d.m;
-		CU(alloc(&d.B, (size_t)d.ldb * m));
+		// B^-1 (the big one: 8 GB at m = 32768) is allocated at first use, i.e. AFTER the upload of A has been put on
+		// the wire, so that the allocation overlaps the DMA instead of preceding it (ensure_B)
 		T* vecs[6];
 		for (auto& v : vecs) CU(alloc(&v, ld));
 		d.b = vecs[0]; hb = vecs[0];
@@ -154,6 +155,7 @@ public:
 		// L2 residency: pin the head of B^-1 in the persisting part of L2 so that it never makes the trip to HBM
 		// (B^-1 is read and rewritten once per pivot; A streams through with evict_first)
 		if (opt.l2_persist_mb >= 0) {
+			CU(ensure_B());
 			int max_persist = 0, max_window = 0;
 			CU(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, opt.device));
 			CU(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, opt.device));
@@ -309,6 +311,7 @@ public:
 			launches++;
 		}
 		CU(cudaEventRecord(ev1, stream));
+		CU(ensure_B());                 // while the copies are on the wire
 		return B200LP_OK;
 	}
 
@@ -334,6 +337,11 @@ public:
 		return reset();
 	}
 
+	cudaError_t ensure_B() {
+		if (d.B) return cudaSuccess;
+		return alloc(&d.B, (size_t)d.ldb * (size_t)d.m);
+	}
+
 	// a launch may still be running: the host mirror of the control block (pending, xepoch, counters) is only
 	// valid after wait()
 	int settle() { return in_flight ? wait(nullptr) : B200LP_OK; }
@@ -342,6 +350,7 @@ public:
 		if (!have_data) return fail(B200LP_ERR_STATE, "reset before upload/generate");
 		CU(cudaSetDevice(opt.device));
 		if (int rc = settle()) return rc;
+		CU(ensure_B());
 		k_reset<T><<<num_sms * 8, 256, 0, stream>>>(d);
 		launches++;
 		if (opt.pricing_rule == 1) {                       // steepest edge: the weights start over with the slack basis
@@ -894,7 +903,7 @@ private:
 	// mid-size LPs whose A and B^-1 fit in the shared memory of the whole grid (one CTA per SM): the resident kernel.
 	// Only with the automatic configuration (an explicit grid, tile shape or pricing path asks for the general kernel).
 	bool resident_ok() const {
-		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || d.prof_cap > 0 || opt.pricing_rule != 0 || opt.ratio_mode == 2 ||
+		if (nranks != 1 || opt.grid_ctas > 0 || opt.mode != 0 || opt.pricing_rule != 0 || opt.ratio_mode == 2 ||
 				opt.tile_shape != 0 || opt.price_mode != 0 || opt.fuse_ratio > 0 || opt.resident < 0)
 			return false;
 		if (d.m < 128) return false;                     // a handful of CTAs: the general kernel on a small grid is as good
@@ -905,6 +914,8 @@ private:
 	int run_resident(int64_t iters) {
 		hc.it_end = hc.iter + iters;
 		CU(push_ctl());
+		if (d.prof_cap > 0) CU(cudaMemsetAsync(d.prof, 0, (size_t)d.prof_cap * NSTAMP * sizeof(unsigned long long), stream));
+		prof_iter0 = hc.iter;
 		d.res_maxG = num_sms;
 		const ResLayout<T> L(d.m, d.ld, d.ns, num_sms);
 		const size_t smem = L.bytes();

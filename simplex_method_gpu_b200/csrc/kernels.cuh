@@ -354,6 +354,8 @@ constexpr int NSTAMP = 16;
 #define PROFILE_NAMES_JSON \
 	"{\"single\": [\"price (+ book2 prologue)\", \"barrier + argmin p\", \"update + FTRAN + ratio groups\", \"barrier\", " \
 	"\"argmin q\", \"book1 (row_q, E_q, dots)\", \"barrier\", \"book2 (x_b, y) [unfused only]\", \"barrier [unfused only]\", \"loop\"], " \
+	"\"resident\": [\"price (shared memory)\", \"barrier + argmin p\", \"a_p from L2, update + FTRAN + ratio (shared memory)\", " \
+	"\"barrier\", \"argmin q\", \"E_q, products, owner: row q out\", \"barrier\", \"row_q / products in, dots, y, x_b\", \"loop\", \"-\"], " \
 	"\"sharded\": [\"price\", \"X1: arrive, publish candidate, gather\", \"fetch a_p + barrier\", " \
 	"\"update + FTRAN\", \"X2: barrier, alpha + ratio of local rows, publish, gather\", " \
 	"\"book1 (E_q, dots; owner: row_q push)\", \"barrier + X3 flag\", \"book2 (x_b, y)\", \"barrier\", \"loop\"]}"
@@ -413,6 +415,32 @@ __device__ __forceinline__ long long reduce_counts(const long long* cnt, int n, 
 	c = 0;
 #pragma unroll
 	for (int w = 0; w < NWARP; ++w) c += sh.red_c[w];
+	return c;
+}
+
+// argmin over the per-CTA candidates and the sum of their counts in one pass (one set of loads and barriers)
+__device__ __forceinline__ long long reduce_cands_counts(const Cand* cand, const long long* cnt, int n, double& v, long long& i, Smem& sh) {
+	v = CUDART_INF; i = LLONG_MAX;
+	long long c = 0;
+	for (int k = threadIdx.x; k < n; k += NT) {
+		const double cv = __ldcg(&cand[k].val);
+		const long long ci = __ldcg(&cand[k].idx);
+		c += __ldcg(&cnt[k]);
+		if (cand_better(cv, ci, v, i)) { v = cv; i = ci; }
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	warp_argmin(v, i);
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+	__syncthreads();
+	if (lane == 0) { sh.red_v[warp] = v; sh.red_i[warp] = i; sh.red_c[warp] = c; }
+	__syncthreads();
+	v = sh.red_v[0]; i = sh.red_i[0]; c = sh.red_c[0];
+#pragma unroll
+	for (int w = 1; w < NWARP; ++w) {
+		if (cand_better(sh.red_v[w], sh.red_i[w], v, i)) { v = sh.red_v[w]; i = sh.red_i[w]; }
+		c += sh.red_c[w];
+	}
 	return c;
 }
 
@@ -1647,7 +1675,7 @@ template <typename T>
 struct ResLayout {
 	static constexpr int SBP = SUBW + 1;     // padded sub-block
 	long long rpc, cpc, nsb, G;              // rows / columns per CTA, sub-blocks per row, CTAs in use
-	long long Bs, As, y, b, rowq, prod, rowqP, apP, part, xb, cb, al, eq, end;   // element offsets (T)
+	long long Bs, As, y, b, rowq, prod, rowqP, apP, part, xb, cb, al, eq, cown, cunit, end;   // element offsets (T)
 	__host__ __device__ static long long r4(long long x) { return (x + 3) / 4 * 4; }
 	__host__ __device__ ResLayout(long long m, long long ld, long long ns, long long maxG) {
 		rpc = (m + maxG - 1) / maxG;
@@ -1661,6 +1689,8 @@ struct ResLayout {
 		Bs = o; o += r4(rpc * nsb * SBP);
 		part = o; o += r4(rpc * nsb);
 		xb = o; o += r4(rpc); cb = o; o += r4(rpc); al = o; o += r4(rpc); eq = o; o += r4(rpc);
+		cown = o; o += r4(cpc);                                   // costs of the own structural columns
+		cunit = o; o += r4(((m > ns ? m : ns) + G - 1) / G + 1);  // costs of the own share of the unit columns
 		end = o;
 	}
 	__host__ __device__ size_t bytes() const { return (size_t)end * sizeof(T) + (size_t)r4(rpc) * sizeof(int) + 16; }
@@ -1669,24 +1699,39 @@ struct ResLayout {
 // sum of a vector of m values held in shared memory in the order of the O(m) dots (256-element slices: thread t
 // owns element t, warp butterfly, 8 warp sums left to right; slices left to right); PROD: the elements are
 // x[i] * y[i] formed by one fma each, otherwise x[i] as they are.  Result in every thread.
-template <typename T, bool PROD>
-__device__ __forceinline__ T res_sliced_sum(const T* x, const T* y, long long m, Smem& sh) {
+// two such sums at once: s1 = sum of x[i] * y[i] (one fma each), s2 = sum of z[i]; six slices (m <= 1536) share
+// one barrier
+template <typename T>
+__device__ __forceinline__ void res_sliced_sums(const T* x, const T* y, const T* z, long long m, Smem& sh, T& s1, T& s2) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	T tot = T(0);
-	for (long long s0 = 0; s0 < m; s0 += SLICE) {
-		const long long i = s0 + tid;
-		T t = T(0);
-		if (i < m) t = PROD ? fma_t(x[i], y[i], T(0)) : x[i];
-		t = warp_butterfly_sum(t);
-		__syncthreads();
-		if (lane == 0) sh.dsum[0][warp] = (double)t;
-		__syncthreads();
-		T a = T(0);
+	constexpr int SPB = 6;                                    // slices per barrier: 2 * SPB <= the 12 slots of a wsum buffer
+	s1 = T(0); s2 = T(0);
+	int buf = 0;
+	for (long long s0 = 0; s0 < m; s0 += (long long)SPB * SLICE, buf ^= 1) {
 #pragma unroll
-		for (int w = 0; w < NWARP; ++w) a = a + (T)sh.dsum[0][w];
-		tot = tot + a;
+		for (int k = 0; k < SPB; ++k) {
+			const long long i = s0 + (long long)k * SLICE + tid;
+			if (s0 + (long long)k * SLICE < m) {               // CTA uniform
+				T t1 = T(0), t2 = T(0);
+				if (i < m) { t1 = fma_t(x[i], y[i], T(0)); t2 = z[i]; }
+				t1 = warp_butterfly_sum(t1);
+				t2 = warp_butterfly_sum(t2);
+				if (lane == 0) { sh.wsum[buf][2 * k][warp] = (double)t1; sh.wsum[buf][2 * k + 1][warp] = (double)t2; }
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < SPB; ++k) {
+			if (s0 + (long long)k * SLICE < m) {
+				T a1 = T(0), a2 = T(0);
+#pragma unroll
+				for (int w = 0; w < NWARP; ++w) { a1 = a1 + (T)sh.wsum[buf][2 * k][w]; a2 = a2 + (T)sh.wsum[buf][2 * k + 1][w]; }
+				s1 = s1 + a1;
+				s2 = s2 + a2;
+			}
+		}
 	}
-	return tot;
+	__syncthreads();
 }
 
 template <typename T>
@@ -1700,7 +1745,7 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 	T* S = reinterpret_cast<T*>(dynraw);
 	const ResLayout<T> L(d.m, d.ld, d.ns, d.res_maxG);
 	T *sA = S + L.As, *sy = S + L.y, *sb = S + L.b, *srq = S + L.rowq, *srqP = S + L.rowqP, *sapP = S + L.apP, *sprod = S + L.prod, *sB = S + L.Bs,
-	  *spart = S + L.part, *sxb = S + L.xb, *scb = S + L.cb, *sal = S + L.al, *seq = S + L.eq;
+	  *spart = S + L.part, *sxb = S + L.xb, *scb = S + L.cb, *sal = S + L.al, *seq = S + L.eq, *scown = S + L.cown, *scunit = S + L.cunit;
 	int* sbix = reinterpret_cast<int*>(S + L.end);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int G = gridDim.x, me = blockIdx.x;          // G == L.G
@@ -1726,6 +1771,8 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 	for (long long r = tid; r < nr; r += NT) {
 		sxb[r] = d.x_b[r0 + r]; scb[r] = d.c_b[r0 + r]; sal[r] = d.alpha[r0 + r]; seq[r] = d.E_q[r0 + r]; sbix[r] = d.b_ixs[r0 + r];
 	}
+	for (long long k = tid; k < nc; k += NT) scown[k] = d.c[c0 + k];
+	for (long long k = k0 + tid; k < k1; k += NT) scunit[k - k0] = d.c[ns + k];
 	long long it = ctl->iter, pivots = ctl->pivots;
 	const long long it_end = ctl->it_end;
 	int pending = ctl->pending;
@@ -1735,8 +1782,10 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 	const T tol = (T)d.pivot_tol;
 	__syncthreads();
 
+	const long long it0 = it;
 	while (it < it_end) {
 		// ---- pricing of the own columns (v4:288-302): the dots of price_phase, operands in shared memory
+		stamp(d, it - it0, 0, me);
 		double best_v = CUDART_INF;
 		long long best_i = LLONG_MAX;
 		int buf = 0;
@@ -1768,19 +1817,21 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 			__syncthreads();
 			if (tid < PRICE_NC && kq + tid < nc) {
 				const long long j = c0 + kq + tid;
-				const double e = (double)(warp_sums<T>(sh, buf, tid) - d.c[j]);
+				const double e = (double)(warp_sums<T>(sh, buf, tid) - scown[kq + tid]);
 				if (cand_better(e, j, best_v, best_i)) { best_v = e; best_i = j; }
 			}
 		}
 		for (long long k = k0 + tid; k < k1; k += NT) {      // unit (slack) columns
-			const double e = (double)(sy[k] - d.c[ns + k]);
+			const double e = (double)(sy[k] - scunit[k - k0]);
 			if (cand_better(e, ns + k, best_v, best_i)) { best_v = e; best_i = ns + k; }
 		}
 		block_argmin(best_v, best_i, sh);
 		if (tid == 0) { d.cand[me].val = best_v; d.cand[me].idx = best_i; }
 		if (me == 0 && tid == 0) ctl->abort_latched = *(volatile int*)&ctl->abort_req;
+		stamp(d, it - it0, 1, me);
 		grid_barrier(ctl, epoch, G);
 		reduce_cands(d.cand, G, min_e, p, sh);
+		stamp(d, it - it0, 2, me);
 		if (__ldcg(&ctl->abort_latched)) { aborted = 1; break; }
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
 
@@ -1796,10 +1847,24 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 			const T er = seq[r];
 			const T *rqp = srqP + sbk * SBP, *app = sapP + sbk * SBP;   // consecutive lanes: stride 33 -> no bank conflicts
 			T acc = T(0);
-			for (int u = 0; u < ncols; ++u) {
-				T x = bp[u];
-				if (pending) { x = fma_t(er, rqp[u], x); bp[u] = x; }
-				acc = fma_t(x, app[u], acc);
+			if (ncols == SUBW) {
+#pragma unroll
+				for (int u0 = 0; u0 < SUBW; u0 += 8) {
+					T x8[8], r8[8], a8[8];
+#pragma unroll
+					for (int u = 0; u < 8; ++u) { x8[u] = bp[u0 + u]; r8[u] = rqp[u0 + u]; a8[u] = app[u0 + u]; }
+#pragma unroll
+					for (int u = 0; u < 8; ++u) {
+						if (pending) { x8[u] = fma_t(er, r8[u], x8[u]); bp[u0 + u] = x8[u]; }
+						acc = fma_t(x8[u], a8[u], acc);
+					}
+				}
+			} else {
+				for (int u = 0; u < ncols; ++u) {
+					T x = bp[u];
+					if (pending) { x = fma_t(er, rqp[u], x); bp[u] = x; }
+					acc = fma_t(x, app[u], acc);
+				}
 			}
 			spart[w] = acc;
 		}
@@ -1832,14 +1897,40 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 			d.cand2[me].val = rv; d.cand2[me].idx = ri; d.cnt[me] = elig;
 			d.cand2[G + me].val = ri != LLONG_MAX ? (double)sal[ri - r0] : 0.0;      // alpha at this CTA's candidate
 		}
+		const T c_p = d.c[p];                                 // (in flight across the barrier)
+		stamp(d, it - it0, 3, me);
 		grid_barrier(ctl, epoch, G);
-		double th;
-		reduce_cands(d.cand2, G, th, q, sh);
-		const long long el = reduce_counts(d.cnt, G, sh);
+		stamp(d, it - it0, 4, me);
+		// one pass: argmin of the candidates, sum of the eligible counts, and alpha at the winner (thread k holds CTA k's record)
+		double th = CUDART_INF, aq = 0.0;
+		q = LLONG_MAX;
+		long long el = 0;
+		for (int k = tid; k < G; k += NT) {
+			const double cv = __ldcg(&d.cand2[k].val), ca = __ldcg(&d.cand2[G + k].val);
+			const long long ci = __ldcg(&d.cand2[k].idx);
+			el += __ldcg(&d.cnt[k]);
+			if (cand_better(cv, ci, th, q)) { th = cv; q = ci; aq = ca; }
+		}
+#pragma unroll
+		for (int off = 16; off >= 1; off >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, th, off), oa = __shfl_xor_sync(0xffffffffu, aq, off);
+			const long long oi = __shfl_xor_sync(0xffffffffu, q, off);
+			el += __shfl_xor_sync(0xffffffffu, el, off);
+			if (cand_better(ov, oi, th, q)) { th = ov; q = oi; aq = oa; }
+		}
+		__syncthreads();
+		if (lane == 0) { sh.red_v[warp] = th; sh.red_i[warp] = q; sh.red_c[warp] = el; sh.dsum[2][warp] = aq; }
+		__syncthreads();
+		th = sh.red_v[0]; q = sh.red_i[0]; el = sh.red_c[0]; aq = sh.dsum[2][0];
+#pragma unroll
+		for (int w = 1; w < NWARP; ++w) {
+			if (cand_better(sh.red_v[w], sh.red_i[w], th, q)) { th = sh.red_v[w]; q = sh.red_i[w]; aq = sh.dsum[2][w]; }
+			el += sh.red_c[w];
+		}
 		if (el == 0) { status = 2; done = 1; ++it; break; }
 		const int owner = (int)(q / L.rpc);
-		const T alpha_q = (T)__ldcg(&d.cand2[G + owner].val);
-		const T c_p = d.c[p];
+		const T alpha_q = (T)aq;
+		stamp(d, it - it0, 5, me);
 
 		// ---- E_q of the own rows, products c_b_new E_q; the owner of row q publishes it (v4:331-332, 340, 354)
 		if (tid < nr) {
@@ -1854,9 +1945,12 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 			const T* brow = sB + (q - r0) * nsb * SBP;
 			for (long long j = tid; j < m; j += NT) d.row_q[j] = brow[(j / SUBW) * SBP + j % SUBW];
 		}
+		stamp(d, it - it0, 6, me);
 		grid_barrier(ctl, epoch, G);
+		stamp(d, it - it0, 7, me);
 
 		// ---- every CTA: row_q.b, c_b.E_q, y (own full copy); own rows: x_b, c_b, b_ixs (v4:339-356)
+		const T c_b_q = (T)__ldcg(&ctl->c_b_q);            // issued with the vector loads below
 		for (long long j = tid; j < ld; j += NT) {
 			const T rq = j < m ? __ldcg(d.row_q + j) : T(0);
 			srq[j] = rq;
@@ -1864,9 +1958,9 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 			sprod[j] = j < m ? __ldcg(d.E_q + j) : T(0);
 		}
 		__syncthreads();
-		const T sx = res_sliced_sum<T, true>(srq, sb, m, sh);
-		T syv = res_sliced_sum<T, false>(sprod, nullptr, m, sh);
-		syv += c_p - (T)__ldcg(&ctl->c_b_q);
+		T sx, syv;
+		res_sliced_sums<T>(srq, sb, sprod, m, sh, sx, syv);
+		syv += c_p - c_b_q;
 		for (long long j = tid; j < m; j += NT) sy[j] = fma_t(syv, srq[j], sy[j]);
 		if (tid < nr) {
 			sxb[tid] = fma_t(sx, seq[tid], sxb[tid]);
@@ -1875,6 +1969,7 @@ __global__ void __launch_bounds__(NT, 1) simplex_resident(Dev<T> d) {
 		if (me == 0 && tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
 		pending = 1;
 		++pivots;
+		stamp(d, it - it0, 8, me);
 		++it;
 		__syncthreads();
 		// (the next exchange through d.E_q / d.row_q is two barriers away: no barrier needed here)
