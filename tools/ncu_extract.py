@@ -4,7 +4,7 @@
     python tools/ncu_extract.py gpurun_out/r01_prof_phases_c3.ncu-rep
 
 Writes profiles/<stem>_summary.txt (one block per profiled launch) and, with --workload, updates
-profiles/r01_traffic.json (dram bytes per pivot of the persistent kernel — bench.py's roofline.traffic).
+profiles/r02_traffic.json (dram bytes per pivot of the persistent kernel — bench.py's roofline.traffic).
 """
 import argparse
 import csv
@@ -50,7 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
     ap.add_argument("--pivots", type=int, default=0, help="pivots per profiled launch (persistent kernel)")
-    ap.add_argument("--workload", default="", help="C3 | C4: update profiles/r01_traffic.json")
+    ap.add_argument("--workload", default="", help="C3 | C4: update profiles/r02_traffic.json")
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
     a = ap.parse_args()
@@ -75,7 +75,7 @@ def main():
             tot = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
             dur = vals["gpu__time_duration.sum"]
             lines.append(f"  {'dram read + write':<34s} {tot / 1e9:.4f} GB  -> {tot / dur / 1e9:.1f} GB/s over the profiled duration")
-            if a.pivots and "simplex_persistent" in name:
+            if a.pivots and ("simplex_" in name):
                 lines.append(f"  {'per pivot (' + str(a.pivots) + ' pivots in this launch)':<34s} {tot / a.pivots / 1e9:.4f} GB dram, "
                              f"{dur / a.pivots * 1e6:.1f} us (under the profiler: serialised replay passes, not a bench number)")
                 traffic = {"dram_bytes_per_pivot": tot / a.pivots, "dram_read_per_pivot": vals["dram__bytes_read.sum"] / a.pivots,
@@ -86,7 +86,7 @@ def main():
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
     if a.workload and traffic:
-        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r02_traffic.json")
         try:
             with open(tj) as f:
                 allt = json.load(f)

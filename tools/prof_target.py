@@ -18,10 +18,28 @@ ap.add_argument("--lp", default="8192x16384")
 ap.add_argument("--pivots", type=int, default=16)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--phases", action="store_true")
+ap.add_argument("--rule", type=int, default=0, help="pricing_rule: 1 = steepest edge")
+ap.add_argument("--emu", type=int, default=0, help="R > 1: R sharded ranks emulated on device 0 in one cooperative launch")
+ap.add_argument("--general", action="store_true", help="resident = -1: force the general kernel on a mid-size LP")
+ap.add_argument("--km", type=int, default=0, help="Klee-Minty cube of this dimension instead of a dense LP (tiny kernel)")
 a = ap.parse_args()
 m, n = (int(x) for x in a.lp.lower().split("x"))
-e = lp.Engine(m, n, np.float64, eps=1e-9, max_iter=1 << 30, mode=1 if a.phases else 0)
-e.generate_dense(1)
+kw = dict(eps=1e-9, max_iter=1 << 30, mode=1 if a.phases else 0, pricing_rule=a.rule)
+if a.general:
+    kw["resident"] = -1
+if a.emu > 1:
+    kw["devices"] = [0] * a.emu
+if a.km:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import oracle  # test infrastructure: only the LP generator is used here
+    A, b, c = oracle.gen_klee_minty(a.km)
+    m, n = A.shape
+    kw["eps"] = 1e-4
+    e = lp.Engine(m, n, np.float64, **kw)
+    e.upload(A, b, c)
+else:
+    e = lp.Engine(m, n, np.float64, **kw)
+    e.generate_dense(1)
 for k in range(a.launches):
     r = e.run(a.pivots)
     print(f"launch {k}: {r['pivots']} pivots total, {r['ms_solve']:.3f} ms, status {int(r['status'])}", flush=True)
