@@ -828,6 +828,26 @@ __device__ __forceinline__ T sum_chunk_partials(const T* part0, long long stride
 }
 
 
+// The same sums for 32 consecutive local rows [il0, il0 + 32) by the whole CTA: warp w loads chunks w, w + 8, ...
+// (one coalesced 32-row segment each, all loads of the CTA in flight together) into `stage` (nchunk x 32), then
+// threads 0..31 add their row's partials left to right from shared memory.  One L2 round trip instead of
+// nchunk / 16 dependent ones per thread; same association as sum_chunk_partials.  Result valid in threads 0..31.
+template <typename T>
+__device__ __forceinline__ T sum_partials_rows32(const Dev<T>& d, T* stage, long long il0) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool in = il0 + lane < d.ldb;
+	for (int c = warp; c < d.nchunk; c += NWARP)
+		stage[c * 32 + lane] = in ? __ldcg(d.alpha_part + (long long)c * d.ldb + il0 + lane) : T(0);
+	__syncthreads();
+	T a = T(0);
+	if (tid < 32) {
+		a = stage[lane];
+		for (int c = 1; c < d.nchunk; ++c) a = a + stage[c * 32 + lane];
+	}
+	__syncthreads();
+	return a;
+}
+
 template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int r);
 
 // tile count of a row group: release at gpu scope (the tile's alpha_part stores, made by other threads of the
@@ -1087,25 +1107,41 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 // over alpha_i > 0 (strict, v4:203); masked argmin + eligible-row count.
 // Replaces cudaMemset + compute_theta + D2H + cub ArgMin (v4:311-325).
 template <typename T, bool FROM_PARTIALS>
-__device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts) {
+__device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts, T* stage = nullptr) {
 	const int tid = threadIdx.x;
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 	long long elig = 0;
-	for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
-		T a;
-		if (FROM_PARTIALS) {
-			a = sum_chunk_partials(d.alpha_part + i, d.ldb, d.nchunk);
-			d.alpha[i] = a;
-		} else {
-			a = d.alpha[i];   // already exchanged between the ranks
-		}
+	auto consider = [&](long long i, T a) {
 		if (a > (T)d.pivot_tol) {
 			++elig;
 			const T xb = ratio_num(d.x_b[i], d.ratio_mode);
 			// Harris, first pass: the widest step the tolerance allows (the row is chosen by harris_phase2)
 			const double th = d.ratio_mode == 2 ? (double)((xb + (T)d.harris_delta) / a) : (double)(xb / a);
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+		}
+	};
+	if (FROM_PARTIALS && stage) {
+		// blocks of 32 rows, the CTA's warps load the chunk partials together (sum_partials_rows32)
+		const long long nblk = (d.m + 31) / 32;
+		for (long long blk = part; blk < nblk; blk += nparts) {
+			const T a = sum_partials_rows32<T>(d, stage, blk * 32);
+			const long long i = blk * 32 + tid;
+			if (tid < 32 && i < d.m) {
+				d.alpha[i] = a;
+				consider(i, a);
+			}
+		}
+	} else {
+		for (long long i = (long long)part * NT + tid; i < d.m; i += (long long)nparts * NT) {
+			T a;
+			if (FROM_PARTIALS) {
+				a = sum_chunk_partials(d.alpha_part + i, d.ldb, d.nchunk);
+				d.alpha[i] = a;
+			} else {
+				a = d.alpha[i];   // already exchanged between the ranks
+			}
+			consider(i, a);
 		}
 	}
 	block_argmin(best_v, best_i, sh);
@@ -1389,7 +1425,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent(Dev<T> d) {
 			stamp(d, it - it0, 3);
 			grid_barrier(ctl, epoch, G);
 			if (me == 0 && threadIdx.x == 0) ctl->upd_ctr = 0;
-			ratio_phase<T, true>(d, sh, me, G);
+			ratio_phase<T, true>(d, sh, me, G, reinterpret_cast<T*>(ringbuf));
 			grid_barrier(ctl, epoch, G);
 			stamp(d, it - it0, 4);
 			reduce_cands(d.cand, G, th, q, sh);
@@ -2142,19 +2178,23 @@ __device__ void fetch_column(const Dev<T>& d, long long p, int part, int nparts)
 // X2 producer: alpha of the local rows = sum of the chunk partials (left to right), stored into
 // every rank's alpha; the ratio test of those rows (v4:199-208) gives this CTA's candidate.
 template <typename T>
-__device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, int part, int nparts) {
+__device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, T* stage, int part, int nparts) {
 	const int tid = threadIdx.x;
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 	long long elig = 0;
-	for (long long il = (long long)part * NT + tid; il < d.ldb; il += (long long)nparts * NT) {
-		const T a = sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk);
-		const long long i = d.row0 + il;
-		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
-		if (i < d.m && a > (T)d.pivot_tol) {
-			++elig;
-			const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
-			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+	const long long nblk = (d.ldb + 31) / 32;           // blocks of 32 local rows (sum_partials_rows32)
+	for (long long blk = part; blk < nblk; blk += nparts) {
+		const T a = sum_partials_rows32<T>(d, stage, blk * 32);
+		const long long il = blk * 32 + tid;
+		if (tid < 32 && il < d.ldb) {
+			const long long i = d.row0 + il;
+			for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
+			if (i < d.m && a > (T)d.pivot_tol) {
+				++elig;
+				const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
+				if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
+			}
 		}
 	}
 	block_argmin(best_v, best_i, sh);
@@ -2272,7 +2312,7 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 			stamp(d, it - it0, 4, me);
 			if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
 			// ---- X2: alpha slices to every rank together with the ratio test of the local rows (v4:311-325)
-			push_alpha_ratio<T>(d, sh, me, G);
+			push_alpha_ratio<T>(d, sh, reinterpret_cast<T*>(ringbuf), me, G);
 			if (arrive_last(&ctl->xarr[1], n2 += G, sh)) publish(d, sh, 1, 0, xe, d.cand, G, d.cnt, 0);
 		}
 		pending = 0;

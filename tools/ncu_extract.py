@@ -40,7 +40,10 @@ SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):                       # raw page already exported on the GPU box (tools/profile_box.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     return hdr, units, data
@@ -57,6 +60,8 @@ def main():
     hdr, units, data = load(a.rep)
     col = {h: i for i, h in enumerate(hdr)}
     stem = os.path.splitext(os.path.basename(a.rep))[0]
+    if stem.endswith("_raw"):
+        stem = stem[:-4]
     lines = [f"# {stem}: ncu --set full --clock-control none, one block per profiled launch (values as ncu reports them)"]
     traffic = None
     for r in data:

@@ -16,12 +16,21 @@ echo "launch list rc=$?"
 # 2. full metric set, steady-state launch (3rd of 3) of every loop kernel:
 #    general persistent kernel at C4 (bench workload) and C3 (roofline config), steepest-edge variant at C3,
 #    shared-memory-resident kernel at C2, tiny kernel (Klee-Minty 20), sharded loop (2 ranks emulated on one device)
+# The reports are ~50 MB each (gpurun brings back 64 MiB at most): the raw page and the hottest source lines are
+# exported to CSV on the box and the .ncu-rep is dropped.
+export_rep() { # $1 = report stem (without .ncu-rep)
+	ncu -i $1.ncu-rep --page raw --csv > $1_raw.csv 2> /dev/null
+	ncu -i $1.ncu-rep --page source --csv > $1_source_full.csv 2> /dev/null
+	python tools/ncu_hot_lines.py $1_source_full.csv 60 > $1_source_top.txt 2> /dev/null
+	rm -f $1.ncu-rep $1_source_full.csv
+}
 prof() { # $1 tag  $2 kernel regex  $3.. target arguments
 	local tag=$1 rx=$2; shift 2
 	local T="python tools/prof_target.py $*"
 	$T > $O/${R}_prof_plain_$tag.log 2>&1 &&
 	ncu --set full --clock-control none --import-source on -k regex:$rx -s 2 -c 1 -f -o $O/${R}_prof_$tag $T > $O/${R}_prof_ncu_$tag.log 2>&1
 	echo "$tag rc=$?"
+	export_rep $O/${R}_prof_$tag
 }
 prof persistent_c4 "simplex_persistent" --lp 32768x65536 --pivots 8 --launches 3
 prof persistent_c3 "simplex_persistent" --lp 8192x16384 --pivots 24 --launches 3
@@ -35,4 +44,5 @@ T="python tools/prof_target.py --lp 8192x16384 --pivots 6 --launches 1 --phases"
 $T > $O/${R}_prof_plain_phases.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_price|k_update_ftran" -s 6 -c 4 -f -o $O/${R}_prof_phases_c3 $T > $O/${R}_prof_ncu_phases.log 2>&1
 echo "phases rc=$?"
+export_rep $O/${R}_prof_phases_c3
 ls -la $O | grep ${R}_
