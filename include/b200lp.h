@@ -65,7 +65,7 @@ typedef struct {
 	int32_t price_cols;   /* pricing group width: 0 = auto, else 2 | 4 columns per TMA block */
 	int32_t l2_persist_mb; /* pin the head of B^-1 in the persisting part of L2: -1 = off (default), 0 = as much as
 	                          the device allows, else MiB */
-	int32_t price_mode;   /* 0 = auto (register-staged loads up to a 2 GB A shard, TMA ring above), 1 = TMA ring, 2 = register-staged */
+	int32_t price_mode;   /* 0 = auto (register-staged loads), 1 = TMA ring (cp.async.bulk + mbarrier), 2 = register-staged */
 	int32_t ratio_group_rows; /* rows of B^-1 whose ratio test runs as one unit inside the update+FTRAN pass: 0 = auto (256) */
 	double  pivot_tol;    /* ratio-test eligibility alpha > pivot_tol; 0 (default) = the reference's strict test (v4:203) */
 	int32_t price_tail;   /* columns at the end of a pricing pass handed out one at a time: 0 = auto, -1 = none, else count */

@@ -771,10 +771,11 @@ private:
 		// more than their shorter tail saves, so auto is always 4)
 		d.price_nc = (opt.price_cols == 2 || opt.price_cols == 4) ? opt.price_cols : 4;
 		// Pricing path (measured): register-staged loads win clearly while the A shard is L2 resident
-		// (the ring's start-up is a third of such a pass), by ~6 % of the pass at m = 8192 (512 MB) and tie with the
-		// TMA ring at 1 GB (8-GPU shard of m = 32768) and 8 GB; the ring is kept for the largest shards.
-		d.price_direct = opt.price_mode == 1 ? 0 : opt.price_mode == 2 ? 1
-		               : ((size_t)d.ld * (size_t)nsl_new * sizeof(T) <= ((size_t)2 << 30) ? 1 : 0);
+		// (the ring's start-up is a third of such a pass) and by ~6 % of the pass at m = 8192.  At 8 GB (m = 32768 on
+		// one GPU) the TMA ring was on a par in round 1 (1215 us against 1243 us per pass); in the round-2 kernel its
+		// loop state no longer fits the 128 registers next to the rest of the loop (ptxas spills it: 1323 us) while
+		// the register-staged pass runs at 1233 us, so auto = register-staged everywhere and the ring is price_mode = 1.
+		d.price_direct = opt.price_mode == 1 ? 0 : 1;
 		if (opt.pricing_rule == 1) d.price_direct = 1;      // the steepest-edge pass is register-staged
 		// x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass: y must fit in the (idle) ring memory
 		// and pricing must read y from there (register-staged path); single GPU only

@@ -1121,9 +1121,11 @@ __device__ void ratio_phase(const Dev<T>& d, Smem& sh, int part, int nparts, T* 
 			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
 	};
-	if (FROM_PARTIALS && stage) {
-		// blocks of 32 rows, the CTA's warps load the chunk partials together (sum_partials_rows32)
-		const long long nblk = (d.m + 31) / 32;
+	const long long nblk = (d.m + 31) / 32;
+	if (FROM_PARTIALS && stage && nblk <= 2 * (long long)nparts) {
+		// blocks of 32 rows, the CTA's warps load the chunk partials together (sum_partials_rows32); only while
+		// every CTA gets at most two blocks (measured at m = 32768 on one GPU, 3.5 blocks per CTA: 20.7 us against
+		// 12.8 us for one row per thread)
 		for (long long blk = part; blk < nblk; blk += nparts) {
 			const T a = sum_partials_rows32<T>(d, stage, blk * 32);
 			const long long i = blk * 32 + tid;
@@ -2183,19 +2185,25 @@ __device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, T* stage, int part, 
 	double best_v = CUDART_INF;
 	long long best_i = LLONG_MAX;
 	long long elig = 0;
-	const long long nblk = (d.ldb + 31) / 32;           // blocks of 32 local rows (sum_partials_rows32)
-	for (long long blk = part; blk < nblk; blk += nparts) {
-		const T a = sum_partials_rows32<T>(d, stage, blk * 32);
-		const long long il = blk * 32 + tid;
-		if (tid < 32 && il < d.ldb) {
-			const long long i = d.row0 + il;
-			for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
-			if (i < d.m && a > (T)d.pivot_tol) {
-				++elig;
-				const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
-				if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
-			}
+	auto take = [&](long long il, T a) {
+		const long long i = d.row0 + il;
+		for (int r = 0; r < d.nranks; ++r) xalpha(d, r)[i] = a;
+		if (i < d.m && a > (T)d.pivot_tol) {
+			++elig;
+			const double th = (double)(ratio_num(d.x_b[i], d.ratio_mode) / a);
+			if (cand_better(th, i, best_v, best_i)) { best_v = th; best_i = i; }
 		}
+	};
+	const long long nblk = (d.ldb + 31) / 32;           // blocks of 32 local rows
+	if (nblk <= 2 * (long long)nparts) {                // the CTA's warps load a block's chunk partials together
+		for (long long blk = part; blk < nblk; blk += nparts) {
+			const T a = sum_partials_rows32<T>(d, stage, blk * 32);
+			const long long il = blk * 32 + tid;
+			if (tid < 32 && il < d.ldb) take(il, a);
+		}
+	} else {                                            // many rows per CTA: one row per thread
+		for (long long il = (long long)part * NT + tid; il < d.ldb; il += (long long)nparts * NT)
+			take(il, sum_chunk_partials(d.alpha_part + il, d.ldb, d.nchunk));
 	}
 	block_argmin(best_v, best_i, sh);
 #pragma unroll
