@@ -22,7 +22,8 @@ MAX_ITER, OPTIMUM, UNBOUNDED, THETA_OVERFLOW = 0, 1, 2, 3
 
 
 class _Opts(C.Structure):
-    _fields_ = [("pivot_tol", C.c_double), ("harris_delta", C.c_double), ("ratio_mode", C.c_int), ("pricing_rule", C.c_int)]
+    _fields_ = [("pivot_tol", C.c_double), ("harris_delta", C.c_double), ("ratio_mode", C.c_int), ("pricing_rule", C.c_int),
+                ("nranks", C.c_int), ("reserved", C.c_int)]
 
 
 class _Result(C.Structure):
@@ -94,7 +95,7 @@ def _ptr(a):
 
 
 def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=None,
-          pivot_tol=0.0, ratio_mode=0, harris_delta=0.0, pricing_rule=0) -> OracleSolution:
+          pivot_tol=0.0, ratio_mode=0, harris_delta=0.0, pricing_rule=0, nranks=1) -> OracleSolution:
     """A: (m, n) array in Fortran (column-major) order, dtype float32/float64; slack block last.
     pivot_tol / ratio_mode / harris_delta / pricing_rule: the modes outside the reference's contract
     (simplex_oracle.h); all zero = the reference's loop."""
@@ -115,7 +116,7 @@ def solve(A, b, c, eps=1e-4, max_iter=5, order=0, want_Binv=False, trace_cap=Non
     gq = np.zeros(cap, np.float64)
     res = _Result()
     fn = lib().oracle_solve_ex_f64 if dt == np.float64 else lib().oracle_solve_ex_f32
-    opts = _Opts(float(pivot_tol), float(harris_delta), int(ratio_mode), int(pricing_rule))
+    opts = _Opts(float(pivot_tol), float(harris_delta), int(ratio_mode), int(pricing_rule), int(nranks), 0)
     rc = fn(_ptr(A), _ptr(b), _ptr(c), m, n, eps, int(max_iter), int(order), C.byref(opts),
             _ptr(x_b), _ptr(b_ixs), _ptr(y), _ptr(Binv), _ptr(tp), _ptr(tq), _ptr(gp), _ptr(gq), cap, C.byref(res))
     if rc != 0:

@@ -46,6 +46,9 @@ typedef struct {
 	double harris_delta;
 	int ratio_mode;
 	int pricing_rule;
+	int nranks;      /* order = 1 with steepest edge on R ranks: v = B^-T alpha is the sum, in rank order, of the column
+	                    dots over each rank's row block (the engine's row partition); 0 / 1 = one block */
+	int reserved;
 } oracle_opts;
 
 /*

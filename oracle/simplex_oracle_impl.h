@@ -130,6 +130,11 @@ int FN(oracle_solve_ex)(const REAL* A, const REAL* b, const REAL* c, long m, lon
 	const REAL harris_delta = opts ? (REAL)opts->harris_delta : (REAL)0;
 	const int ratio_mode = opts ? opts->ratio_mode : 0;
 	const int steepest = opts ? opts->pricing_rule == 1 : 0;
+	const int nranks = opts && opts->nranks > 1 ? opts->nranks : 1;
+	/* the engine's row partition of B^-1 (Engine ctor in engine.cu): equal blocks of whole warp-wide vector rows */
+	const long rowq = 32 * (16 / (long)sizeof(REAL));
+	const long ld_e = (m + rowq - 1) / rowq * rowq;
+	const long rpr = ((ld_e + nranks - 1) / nranks + rowq - 1) / rowq * rowq;
 
 	const long chunk = 256; /* engine FTRAN chunk width (order = 1) */
 	REAL* Binv = (REAL*)calloc((size_t)m * m, sizeof(REAL));
@@ -304,7 +309,17 @@ int FN(oracle_solve_ex)(const REAL* A, const REAL* b, const REAL* c, long m, lon
 			#pragma omp parallel for schedule(static)
 			for (long j = 0; j < m; ++j) {
 				const REAL* bc = Binv + j * m;
-				vbt[j] = order == 0 ? FN(dot_seq)(alpha, bc, m, (REAL)0) : FN(dot_block256)(bc, alpha, m);
+				if (order == 0) vbt[j] = FN(dot_seq)(alpha, bc, m, (REAL)0);
+				else {
+					REAL acc = (REAL)0;
+					for (int r = 0; r < nranks; ++r) {
+						const long i0 = (long)r * rpr < m ? (long)r * rpr : m;
+						const long i1 = (long)(r + 1) * rpr < m ? (long)(r + 1) * rpr : m;
+						const REAL part = FN(dot_block256)(bc + i0, alpha + i0, i1 - i0);
+						acc = r == 0 ? part : acc + part;
+					}
+					vbt[j] = acc;
+				}
 			}
 			gamma_p = (REAL)1 + (order == 0 ? FN(dot_seq)(alpha, alpha, m, (REAL)0) : FN(dot_sliced)(alpha, alpha, m));
 		}

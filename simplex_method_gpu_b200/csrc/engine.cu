@@ -122,7 +122,10 @@ public:
 		d.b = vecs[0]; hb = vecs[0];
 		d.y = vecs[1]; d.x_b = vecs[2]; d.c_b = vecs[3]; d.E_q = vecs[4]; d.acol = vecs[5];
 		// mailbox: [XHdr][alpha ld][row_q ld][row_q.b slice partials]; peers store into it in sharded mode (IPC-exported)
-		mbox_bytes = sizeof(XHdr) + (2 * ld + (size_t)d.nslice + 64) * sizeof(T);
+		// steepest edge on several ranks: + R partial vectors of v = B^-T alpha (X4)
+		const size_t rqb_len = ((size_t)d.nslice + 64 + 3) / 4 * 4;
+		d.vpart_off = (long long)(2 * ld + rqb_len);
+		mbox_bytes = sizeof(XHdr) + (2 * ld + rqb_len + (opt.pricing_rule == 1 && nranks > 1 ? (size_t)nranks * ld : 0)) * sizeof(T);
 		CU(alloc(&mbox, mbox_bytes));
 		CU(cudaMemsetAsync(mbox, 0, mbox_bytes, stream));
 		d.alpha = reinterpret_cast<T*>(mbox + sizeof(XHdr));
@@ -135,7 +138,6 @@ public:
 		CU(alloc(&d.dpart, (size_t)3 * d.nslice));
 		d.pricing_rule = opt.pricing_rule;
 		if (opt.pricing_rule == 1) {
-			if (nranks > 1) return fail(B200LP_ERR_ARG, "steepest-edge pricing (pricing_rule = 1) is single-GPU only");
 			if (opt.mode != 0) return fail(B200LP_ERR_ARG, "steepest-edge pricing needs the persistent kernel (mode = 0)");
 			CU(alloc(&d.gamma, (size_t)d.n));
 			CU(alloc(&d.vbt, ld));
@@ -181,12 +183,15 @@ public:
 				(const void*)simplex_persistent<T, 4>, (const void*)simplex_persistent<T, 8>,
 				(const void*)simplex_persistent_sharded<T, 1>, (const void*)simplex_persistent_sharded<T, 2>,
 				(const void*)simplex_persistent_sharded<T, 4>, (const void*)simplex_persistent_sharded<T, 8>,
+				(const void*)simplex_persistent_sharded<T, 1, true>, (const void*)simplex_persistent_sharded<T, 2, true>,
+				(const void*)simplex_persistent_sharded<T, 4, true>, (const void*)simplex_persistent_sharded<T, 8, true>,
 				(const void*)simplex_persistent<T, 1, true>, (const void*)simplex_persistent<T, 2, true>,
 				(const void*)simplex_persistent<T, 4, true>, (const void*)simplex_persistent<T, 8, true>,
 				(const void*)k_price<T>})
 			CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM_BYTES));
 		int occ = 0;
-		if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, DYN_SMEM_BYTES));
+		if (nranks > 1 && opt.pricing_rule == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1, true>, NT, DYN_SMEM_BYTES));
+		else if (nranks > 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent_sharded<T, 1>, NT, DYN_SMEM_BYTES));
 		else if (opt.pricing_rule == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1, true>, NT, DYN_SMEM_BYTES));
 		else            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simplex_persistent<T, 1>, NT, DYN_SMEM_BYTES));
 		if (occ < 1) return fail(B200LP_ERR_CUDA, "persistent kernel does not fit on an SM");
@@ -396,10 +401,16 @@ public:
 		const void* fn;
 		if (nranks > 1) {
 			if (!peers_mapped) return fail(B200LP_ERR_STATE, "sharded engine: peers are not mapped (ipc_import / create_multi)");
-			fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1>
-			   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2>
-			   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4>
-			             : (const void*)simplex_persistent_sharded<T, 8>;
+			if (opt.pricing_rule == 1)
+				fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1, true>
+				   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2, true>
+				   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4, true>
+				             : (const void*)simplex_persistent_sharded<T, 8, true>;
+			else
+				fn = wc == 1 ? (const void*)simplex_persistent_sharded<T, 1>
+				   : wc == 2 ? (const void*)simplex_persistent_sharded<T, 2>
+				   : wc == 4 ? (const void*)simplex_persistent_sharded<T, 4>
+				             : (const void*)simplex_persistent_sharded<T, 8>;
 		} else if (opt.pricing_rule == 1) {
 			fn = wc == 1 ? (const void*)simplex_persistent<T, 1, true>
 			   : wc == 2 ? (const void*)simplex_persistent<T, 2, true>
@@ -1182,7 +1193,10 @@ private:
 	static int only_single(const char* what) { return fail(B200LP_ERR_STATE, std::string(what) + " is not available on a multi-GPU handle"); }
 	int settle_all() { for (auto* e : eng) if (int rc = e->settle()) return rc; return B200LP_OK; }
 
-	const void* emu_fn() const { return (const void*)simplex_persistent_sharded_emu<T, 8>; }
+	const void* emu_fn() const {
+		return eng[0]->opt.pricing_rule == 1 ? (const void*)simplex_persistent_sharded_emu<T, 8, true>
+		                                      : (const void*)simplex_persistent_sharded_emu<T, 8>;
+	}
 
 	int upload_all(const void* A, long long ns_new, const void* b, const void* c) {
 		std::vector<int> rcs(R, 0);

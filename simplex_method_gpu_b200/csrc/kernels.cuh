@@ -148,6 +148,7 @@ struct Dev {
 	long long prof_cap;               // iterations the buffer holds (0 = profiling off)
 	const T* A_peer[MAXR];            // every rank's A shard (peer-mapped over NVLink)
 	unsigned char* mbox_peer[MAXR];   // every rank's mailbox: [XHdr][alpha ld][row_q ld][rqb nslice]; alpha/row_q above point into our own
+	long long vpart_off;              // steepest edge, sharded: element offset (from alpha) of the R partial-v vectors in a mailbox
 	const T* dpart0;                  // row_q.b slice partials: dpart on one GPU, the mailbox's rqb when sharded
 	T* acol;                          // local copy of the entering column (sharded mode only)
 };
@@ -159,13 +160,16 @@ struct XCand {
 	double val;
 	long long idx;
 	long long cnt;
+	double val2;                      // steepest edge: the weighted candidate (-e^2/gamma, index) rides beside (min e, index)
+	long long idx2;
 	unsigned long long flag;
 };
 struct XHdr {
 	XCand pc[2][MAXR];                // X1: pricing candidate of rank r (double buffered by round parity)
 	XCand rc[MAXR];                   // X2: ratio candidate + eligible count of rank r's rows; flag also says "alpha slice stored"
 	unsigned long long rflag;         // X3: row q and its row_q.b slice partials are stored
-	unsigned long long pad[31];
+	unsigned long long vflag[MAXR];   // X4 (steepest edge): rank r's partial of v = B^-T alpha is stored
+	unsigned long long pad[7];
 };
 static_assert(sizeof(XHdr) % 256 == 0, "mailbox vectors must stay 16-byte aligned");
 
@@ -252,6 +256,8 @@ struct Smem {
 	double xv[MAXR];                  // sharded: records gathered from the mailbox
 	long long xi[MAXR];
 	long long xc[MAXR];
+	double xv2[MAXR];
+	long long xi2[MAXR];
 	// pricing ring: TMA bulk copies land in dynamic shared memory, one mbarrier pair per stage
 	unsigned long long full[PRICE_MAX_STAGES];
 	unsigned long long empty[PRICE_MAX_STAGES];
@@ -2119,25 +2125,30 @@ template <typename T> __device__ __forceinline__ XHdr* xhdr(const Dev<T>& d, int
 template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int r) { return reinterpret_cast<T*>(d.mbox_peer[r] + sizeof(XHdr)); }
 template <typename T> __device__ __forceinline__ T* xrowq(const Dev<T>& d, int r) { return xalpha(d, r) + d.ld; }
 template <typename T> __device__ __forceinline__ T* xrqb(const Dev<T>& d, int r) { return xalpha(d, r) + 2 * d.ld; }
+// rank `src`'s partial of v = B^-T alpha in rank `dst`'s mailbox (steepest edge)
+template <typename T> __device__ __forceinline__ T* xvpart(const Dev<T>& d, int dst, int src) { return xalpha(d, dst) + d.vpart_off + (long long)src * d.ld; }
 
 // collect the R records of one exchange from our own mailbox and reduce them: lexicographic
 // argmin over (val, idx), sum of cnt.  Same fixed order on every rank and CTA.
 template <typename T>
 __device__ __forceinline__ bool gather_records(const Dev<T>& d, const XCand* rec, unsigned long long e, Smem& sh,
-		double& v, long long& i, long long& c) {
+		double& v, long long& i, long long& c, double* v2 = nullptr, long long* i2 = nullptr) {
 	if (threadIdx.x < d.nranks) {
 		const XCand* r = rec + threadIdx.x;
 		const bool ok = wait_flag_sys(&r->flag, e);
 		sh.xv[threadIdx.x] = __ldcg(&r->val);
 		sh.xi[threadIdx.x] = __ldcg(&r->idx);
 		sh.xc[threadIdx.x] = ok ? __ldcg(&r->cnt) : -1;
+		if (v2) { sh.xv2[threadIdx.x] = __ldcg(&r->val2); sh.xi2[threadIdx.x] = __ldcg(&r->idx2); }
 	}
 	__syncthreads();
 	v = CUDART_INF; i = LLONG_MAX; c = 0;
+	if (v2) { *v2 = CUDART_INF; *i2 = LLONG_MAX; }
 	bool ok = true;
 	for (int r = 0; r < d.nranks; ++r) {
 		if (sh.xc[r] < 0) ok = false;
 		if (cand_better(sh.xv[r], sh.xi[r], v, i)) { v = sh.xv[r]; i = sh.xi[r]; }
+		if (v2 && cand_better(sh.xv2[r], sh.xi2[r], *v2, *i2)) { *v2 = sh.xv2[r]; *i2 = sh.xi2[r]; }
 		c += sh.xc[r];
 	}
 	__syncthreads();
@@ -2149,9 +2160,10 @@ __device__ __forceinline__ bool gather_records(const Dev<T>& d, const XCand* rec
 // (X1: this rank's abort request, so that all ranks stop in the same iteration).
 template <typename T>
 __device__ __forceinline__ void publish(const Dev<T>& d, Smem& sh, int which, int par, unsigned long long e,
-		const Cand* cands, int ncand, const long long* cnts, long long extra) {
-	double v; long long i;
+		const Cand* cands, int ncand, const long long* cnts, long long extra, const Cand* cands2 = nullptr) {
+	double v, v2 = CUDART_INF; long long i, i2 = LLONG_MAX;
 	reduce_cands(cands, ncand, v, i, sh);
+	if (cands2) reduce_cands(cands2, ncand, v2, i2, sh);
 	const long long c = cnts ? reduce_counts(cnts, ncand, sh) : extra;
 	if (threadIdx.x < d.nranks) {
 		XHdr* h = xhdr(d, threadIdx.x);
@@ -2159,6 +2171,8 @@ __device__ __forceinline__ void publish(const Dev<T>& d, Smem& sh, int which, in
 		dst->val = v;
 		dst->idx = i;
 		dst->cnt = c;
+		dst->val2 = v2;
+		dst->idx2 = i2;
 		st_release_sys(&dst->flag, e);     // orders the three stores above (and, cumulatively, everything
 		                                   // the other CTAs fenced before they arrived) before the flag
 	}
@@ -2224,7 +2238,7 @@ __device__ void push_alpha_ratio(const Dev<T>& d, Smem& sh, T* stage, int part, 
 // book1, sharded: E_q and the c_b.E_q slice partials on every rank (replicated data);
 // X3 producer: the owner of row q gathers it from its B^-1 block, forms the row_q.b slice
 // partials and stores both into every rank's mailbox.
-template <typename T>
+template <typename T, bool SE = false>
 __device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long q, int part, int nparts) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const T alpha_q = __ldcg(d.alpha + q);     // mailbox data: read at L2
@@ -2232,13 +2246,18 @@ __device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long 
 	const bool owner = q >= d.row0 && q < d.row0 + d.ldb;
 	for (long long s = part; s < d.nslice; s += nparts) {
 		const long long i = s * SLICE + tid;
-		T t1 = T(0), t2 = T(0);
+		T t1 = T(0), t2 = T(0), t3 = T(0);
 		if (i < d.m) {
-			const T eq = (i != q) ? (-__ldcg(d.alpha + i) / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
+			const T al = __ldcg(d.alpha + i);
+			const T eq = (i != q) ? (-al / alpha_q) : (T)(1.0 / (double)alpha_q - 1.0);
 			d.E_q[i] = eq;
 			T cb = d.c_b[i];
-			if (i == q) { d.ctl->c_b_q = (double)cb; cb = c_p; }
+			if (i == q) {
+				d.ctl->c_b_q = (double)cb; cb = c_p;
+				if (SE) { d.ctl->alpha_q = (double)alpha_q; d.ctl->leaving = d.b_ixs[q]; }
+			}
 			t2 = fma_t(cb, eq, T(0));
+			if (SE) t3 = fma_t(al, al, T(0));
 			if (owner) {
 				const T rq = d.B[(q - d.row0) + i * d.ldb];
 				t1 = fma_t(rq, d.b[i], T(0));
@@ -2247,17 +2266,45 @@ __device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long 
 		}
 		t1 = warp_butterfly_sum(t1);
 		t2 = warp_butterfly_sum(t2);
+		if (SE) t3 = warp_butterfly_sum(t3);
 		__syncthreads();
-		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; }
+		if (lane == 0) { sh.dsum[0][warp] = (double)t1; sh.dsum[1][warp] = (double)t2; if (SE) sh.dsum[2][warp] = (double)t3; }
 		__syncthreads();
 		if (tid == 0) {
-			T a1 = T(0), a2 = T(0);
+			T a1 = T(0), a2 = T(0), a3 = T(0);
 #pragma unroll
-			for (int w = 0; w < NWARP; ++w) { a1 = a1 + (T)sh.dsum[0][w]; a2 = a2 + (T)sh.dsum[1][w]; }
+			for (int w = 0; w < NWARP; ++w) { a1 = a1 + (T)sh.dsum[0][w]; a2 = a2 + (T)sh.dsum[1][w]; if (SE) a3 = a3 + (T)sh.dsum[2][w]; }
 			d.dpart[(long long)d.nslice + s] = a2;
+			if (SE) d.dpart[2LL * d.nslice + s] = a3;
 			if (owner)
 				for (int r = 0; r < d.nranks; ++r) xrqb(d, r)[s] = a1;
 		}
+	}
+}
+
+// steepest edge, sharded: this rank's partial of v = B^-T alpha — the column dots of its row block of B^-1 with its
+// slice of alpha (pricing order over the local rows) — stored into every rank's mailbox (X4)
+template <typename T>
+__device__ void btran_partial_push(const Dev<T>& d, Smem& sh, int part, int nparts) {
+	const int tid = threadIdx.x;
+	const long long c1 = d.m;
+	const long long nq = c1 / PRICE_NC;
+	const long long nitems = nq + (c1 - nq * PRICE_NC);
+	const T* const vec[3] = {d.alpha + d.row0, nullptr, nullptr};
+	int buf = 0;
+	for (long long g = part; g < nitems; buf ^= 1) {
+		if (tid == 0) sh.tk = (long long)nparts + atomicAdd(&d.ctl->btran_ctr, 1u);
+		const bool quad = g < nq;
+		const long long col = quad ? g * PRICE_NC : nq * PRICE_NC + (g - nq);
+		if (quad) column_dots<T, PRICE_NC, 4, 1, true>(d.B + col * d.ldb, d.ldb, d.ldb, vec, sh, buf);
+		else      column_dots<T, 1, 16, 1, true>(d.B + col * d.ldb, d.ldb, d.ldb, vec, sh, buf);
+		__syncthreads();
+		g = sh.tk;
+		if (tid < (quad ? PRICE_NC : 1)) {
+			const T v = warp_sums<T>(sh, buf, tid);
+			for (int r = 0; r < d.nranks; ++r) xvpart(d, r, d.rank)[col + tid] = v;
+		}
+		__syncthreads();
 	}
 }
 
@@ -2266,7 +2313,10 @@ __device__ void book1_sharded(const Dev<T>& d, Smem& sh, long long p, long long 
 // Per pivot: X1 after pricing, the entering column fetch + one local barrier, the update + FTRAN pass whose row
 // groups push their alpha slices to every rank and run their ratio test as they complete, X2 (one record per
 // rank), book1 + local barrier + X3, book2 + local barrier.
-template <typename T, int WC>
+// SE: steepest-edge pricing (section "steepest-edge pricing" above).  gamma is column-sharded like A, so the weight
+// recurrence needs no exchange; v = B^-T alpha does (X4): every rank pushes the column sums over ITS rows to all ranks
+// beside book1, the v-flag goes out with the X3 flag, and book2 adds the R partials in rank order.
+template <typename T, int WC, bool SE>
 __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, Ring& rcons, Ring& rprod, const int G, const int me) {
 	Ctl* ctl = d.ctl;
 	const int tid = threadIdx.x;
@@ -2281,6 +2331,7 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 	long long p = ctl->p, q = ctl->q;
 	double min_e = ctl->min_e;
 	const XHdr* mine = xhdr(d, d.rank);
+	bool pendg = SE && ctl->se_pending != 0;
 
 	const long long it0 = it;
 	while (it < it_end) {
@@ -2288,14 +2339,28 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 		stamp(d, it - it0, 0, me);
 		++xe;
 		const int par = (int)(xe & 1);
-		if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, me, G);
-		else                price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
+		if (SE) {
+			SeUpd u;
+			u.on = pendg;
+			u.p = p;
+			u.leaving = pendg ? __ldcg(&ctl->leaving) : -1;
+			u.alpha_q = pendg ? __ldcg(&ctl->alpha_q) : 1.0;
+			T gp = T(0);
+			if (pendg) { T sx_, sy_; book2_scalars<T, true>(d, sh, p, sx_, sy_, &gp); }
+			u.gamma_p = (double)gp;
+			const T* const vec[3] = {d.y, d.row_q, d.vbt};
+			price_phase_se<T>(d, sh, vec, u, me, G);
+		} else if (d.price_direct) price_phase_direct<T>(d, sh, nullptr, me, G);
+		else                       price_phase<T>(d, sh, ringbuf, rcons, rprod, me, G);
 		stamp(d, it - it0, 1, me);
 		if (arrive_last(&ctl->xarr[0], n1 += G, sh))
-			publish(d, sh, 0, par, xe, d.cand, G, nullptr, (long long)*(volatile int*)&ctl->abort_req);
+			publish(d, sh, 0, par, xe, d.cand, G, nullptr, (long long)*(volatile int*)&ctl->abort_req, SE ? d.cand2 : nullptr);
 		long long stop;
-		if (!gather_records(d, mine->pc[par], xe, sh, min_e, p, stop)) { bad = 1; break; }
-		if (me == 0 && tid == 0) ctl->price_ctr = 0;       // every local CTA is past pricing
+		double sc;
+		long long pse;
+		if (!gather_records(d, mine->pc[par], xe, sh, min_e, p, stop, SE ? &sc : nullptr, SE ? &pse : nullptr)) { bad = 1; break; }
+		if (SE) { if (pse != LLONG_MAX) p = pse; pendg = false; }
+		if (me == 0 && tid == 0) { ctl->price_ctr = 0; if (SE) ctl->btran_ctr = 0; }   // every local CTA is past pricing
 		stamp(d, it - it0, 2, me);
 		if (stop > 0) { aborted = 1; break; }              // some rank was asked to stop: all ranks see the same sum
 		if (min_e >= -d.eps) { status = 1; done = 1; ++it; break; }
@@ -2332,15 +2397,32 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 		if (elig == 0) { status = 2; done = 1; ++it; break; }
 
 		// ---- pivot: E_q everywhere, X3 row q from its owner, then the replicated O(m) updates
-		book1_sharded<T>(d, sh, p, q, me, G);
+		book1_sharded<T, SE>(d, sh, p, q, me, G);
+		if (SE) btran_partial_push<T>(d, sh, me, G);       // X4 payload: v-partials of the local rows into every mailbox
 		stamp(d, it - it0, 6, me);
 		if (!grid_barrier_t(ctl, epoch, sh, G)) { bad = 1; break; }
 		// owner: the row and its partials were stored by all local CTAs before the barrier; one
 		// system-scope release covers them (release is cumulative over what the barrier acquired)
 		if (me == 0 && tid < d.nranks && q >= d.row0 && q < d.row0 + d.ldb) st_release_sys(&xhdr(d, tid)->rflag, xe);
+		if (SE && me == 0 && tid < d.nranks) st_release_sys(&xhdr(d, tid)->vflag[d.rank], xe);   // X4: same barrier, same release
 		if (tid == 0) sh.bc_c = wait_flag_sys(&mine->rflag, xe);
 		__syncthreads();
 		if (!sh.bc_c) { bad = 1; break; }
+		if (SE) {
+			__syncthreads();
+			if (tid == 0) sh.bc_c = 1;
+			__syncthreads();
+			if (tid < d.nranks && !wait_flag_sys(&mine->vflag[tid], xe)) sh.bc_c = 0;
+			__syncthreads();
+			if (!sh.bc_c) { bad = 1; break; }
+			// v = sum of the R partials in rank order (same on every rank); read again a barrier from here
+			for (long long j = (long long)me * NT + tid; j < d.m; j += (long long)G * NT) {
+				T a = __ldcg(xvpart(d, d.rank, 0) + j);
+				for (int r = 1; r < d.nranks; ++r) a = a + __ldcg(xvpart(d, d.rank, r) + j);
+				d.vbt[j] = a;
+			}
+			pendg = true;
+		}
 		stamp(d, it - it0, 7, me);
 		book2_phase<T>(d, sh, p, q, me, G);
 		if (me == 0 && tid == 0 && pivots < d.trace_cap) d.trace[pivots] = make_int2((int)p, (int)q);
@@ -2359,24 +2441,25 @@ __device__ void sharded_loop(const Dev<T>& d, Smem& sh, unsigned char* ringbuf, 
 			ctl->iter = it; ctl->pivots = pivots; ctl->pending = pending;
 			ctl->status = status; ctl->done = done; ctl->xepoch = xe; ctl->aborted = aborted;
 			ctl->p = p; ctl->q = q; ctl->min_e = min_e; ctl->z = z;
+			if (SE) ctl->se_pending = pendg ? 1 : 0;
 		}
 	}
 }
 
-template <typename T, int WC>
+template <typename T, int WC, bool SE = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded(Dev<T> d) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
 	Ring rcons, rprod;
 	ring_init(sh, rcons, rprod, d.price_nc);
-	sharded_loop<T, WC>(d, sh, ringbuf, rcons, rprod, gridDim.x, blockIdx.x);
+	sharded_loop<T, WC, SE>(d, sh, ringbuf, rcons, rprod, gridDim.x, blockIdx.x);
 }
 
 // Several ranks on ONE device (tests on a single-GPU box, b200lp_create_multi with a repeated device): the
 // ranks' CTA groups are slices of one cooperative grid, so they are co-resident by construction — separate
 // launches that spin on each other must never share a GPU.  Same loop, same mailboxes, same flags; the "peer"
 // pointers are plain device pointers.  R ranks x (gridDim.x / R) CTAs.
-template <typename T, int WC>
+template <typename T, int WC, bool SE = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded_emu(const Dev<T>* devs, int R) {
 	__shared__ Smem sh;
 	extern __shared__ __align__(128) unsigned char ringbuf[];
@@ -2384,7 +2467,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) simplex_persistent_sharded_emu(c
 	const Dev<T>& d = devs[blockIdx.x / Gr];
 	Ring rcons, rprod;
 	ring_init(sh, rcons, rprod, d.price_nc);
-	sharded_loop<T, WC>(d, sh, ringbuf, rcons, rprod, Gr, blockIdx.x % Gr);
+	sharded_loop<T, WC, SE>(d, sh, ringbuf, rcons, rprod, Gr, blockIdx.x % Gr);
 }
 
 // ---------------------------------------------------------------- stand-alone phase kernels

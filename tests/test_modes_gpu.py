@@ -71,9 +71,41 @@ def test_steepest_edge_rejected_where_unsupported(engine_lib):
     with pytest.raises(capi.B200LPError):
         lp.Engine(64, 128, pricing_rule=1, mode=1)
     with pytest.raises(capi.B200LPError):
-        lp.Engine(64, 128, pricing_rule=1, devices=[0, 0])
-    with pytest.raises(capi.B200LPError):
         lp.Engine(64, 128, pricing_rule=7)
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+def test_steepest_edge_sharded_bit_exact_against_oracle(oracle, engine_lib, ranks):
+    """Steepest edge on several ranks (emulated on one device here, real peers where there are any): gamma is
+    column-sharded like A, v = B^-T alpha is the rank-ordered sum of the ranks' partial column sums (exchange X4).  The
+    oracle replays exactly that association (nranks), so the traces must be equal bit for bit; the optimum equals the
+    single-GPU steepest-edge and Dantzig optima to 1e-9."""
+    import torch
+    import simplex_method_gpu_b200 as lp
+    layouts = [[0] * ranks]
+    if torch.cuda.device_count() >= ranks:
+        layouts.append(list(range(ranks)))
+    for name, (A, b, c), eps in (("dense 300x700", oracle.gen_dense(300, 700, 2), 1e-9),
+                                 ("dense 1024x2048", oracle.gen_dense(1024, 2048, 1), 1e-9),
+                                 ("dense 96x1000", oracle.gen_dense(96, 1000, 4), 1e-9),
+                                 ("assignment 16", oracle.gen_assignment(16, 1)[:3], 1e-4)):
+        ref = oracle.solve(A, b, c, eps=eps, max_iter=1 << 20, order=1, pricing_rule=1, nranks=ranks)
+        one = lp.solve(A, b, c, eps=eps, max_iter=1 << 20, pricing_rule=1)
+        for devs in layouts:
+            sol = lp.solve(A, b, c, eps=eps, max_iter=1 << 20, pricing_rule=1, devices=devs)
+            _same(sol, ref, f"{name} devices={devs}")
+            assert abs(sol.z - one.z) <= 1e-9 * max(1.0, abs(one.z))
+    # windows: the pending recurrence and the exchange epochs cross launch boundaries
+    A, b, c = oracle.gen_dense(640, 1400, 5)
+    ref = oracle.solve(A, b, c, eps=1e-9, max_iter=1 << 20, order=1, pricing_rule=1, nranks=ranks)
+    with lp.Engine(640, 1400, np.float64, eps=1e-9, max_iter=1 << 20, pricing_rule=1, devices=[0] * ranks) as e:
+        e.upload(A, b, c)
+        r = e.run(3)
+        while r["status"] == lp.SolveStatus.MaxIter:
+            r = e.run(41)
+        assert r["pivots"] == ref.pivots and r["z"] == ref.z
+        tr = e.trace()
+        assert tr[:, 0].tolist() == ref.trace_p.tolist() and tr[:, 1].tolist() == ref.trace_q.tolist()
 
 
 @pytest.mark.parametrize("tol", [1e-9, 1e-3])

@@ -25,6 +25,7 @@ ap.add_argument("--lp", default="8192x16384")
 ap.add_argument("--window", type=int, default=20000)
 ap.add_argument("--max-pivots", type=int, default=1 << 40)
 ap.add_argument("--no-certificate", action="store_true")
+ap.add_argument("--rule", type=int, default=0, help="pricing_rule: 0 Dantzig (the reference's), 1 steepest edge")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 m, n = (int(x) for x in a.lp.lower().split("x"))
@@ -38,12 +39,12 @@ if world > 1:
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    e = ShardedEngine(m, n, np.float64, rank=rank, world=world, device=local, eps=EPS, max_iter=1 << 40)
+    e = ShardedEngine(m, n, np.float64, rank=rank, world=world, device=local, eps=EPS, max_iter=1 << 40, pricing_rule=a.rule)
     e.generate_dense(SEED)
     e.connect()
     dist.barrier()
 else:
-    e = lp.Engine(m, n, np.float64, eps=EPS, max_iter=1 << 40)
+    e = lp.Engine(m, n, np.float64, eps=EPS, max_iter=1 << 40, pricing_rule=a.rule)
     e.generate_dense(SEED)
 
 ms, t0, windows = 0.0, time.perf_counter(), []
@@ -62,6 +63,7 @@ if world > 1:
     ms = float(t.item())
 x_b, b_ixs, y = e.download()
 res = {"workload": f"dense LP m={m} n={n}, seed {SEED}, eps {EPS}, slack basis to optimum", "n_gpus": world,
+       "pricing_rule": "steepest edge (Goldfarb-Reid recurrence)" if a.rule else "Dantzig (the reference's rule)",
        "status": int(r["status"]), "pivots": int(r["pivots"]), "iterations": int(r["iterations"]), "z": r["z"],
        "seconds_device": ms * 1e-3, "seconds_wall": wall, "pivots_per_s": r["pivots"] / (ms * 1e-3),
        "window": a.window, "progress": windows[:: max(1, len(windows) // 12)]}
