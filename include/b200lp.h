@@ -76,7 +76,7 @@ typedef struct {
 	                         phase of its own after a grid barrier) */
 	int32_t pricing_rule; /* 0 = Dantzig, the reference's rule (v4:288-302); 1 = steepest edge with the Goldfarb-Reid
 	                         recurrence (the reference's to-do list, README.md:16-17): a different pivot sequence, far
-	                         fewer pivots, one more read of B^-1 per pivot; single GPU, persistent kernel */
+	                         fewer pivots, one more read of B^-1 per pivot (and, sharded, one more exchange); persistent kernels */
 	int32_t ratio_mode;   /* ratio test (the reference's open items, README.md:29-30): 0 = textbook, the reference's
 	                         (v4:199-208); 1 = bounded: theta = max(x_b, 0) / alpha, a slightly negative x_b never
 	                         yields a negative step; 2 = Harris two-pass: theta_max = min (max(x_b,0) + harris_delta) / alpha,
