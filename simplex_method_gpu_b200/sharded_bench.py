@@ -97,6 +97,33 @@ def run(args, wl, seed, eps):
                        "b200lp_upload_columns, runs the window and reads x_b / b_ixs back; device buffers are kept "
                        "between steps (handle API) — compare with the single-GPU arm's e2e_cached"}
 
+    # ---- time to optimal with steepest-edge pricing on all ranks (options.pricing_rule = 1; same optimum, far fewer pivots)
+    tto_se = None
+    if getattr(args, "tto_se", "") and args.workload in args.tto_se.split(","):
+        eng.close()
+        eng = ShardedEngine(m, n, np.float64, rank=rank, world=world, device=local, eps=eps, max_iter=1 << 40, pricing_rule=1)
+        eng.generate_dense(seed)
+        eng.connect()
+        dist.barrier()
+        eng.run(4)
+        eng.reset()
+        dist.barrier()
+        t0 = time.perf_counter()
+        rs = eng.run(1 << 40)
+        wall = time.perf_counter() - t0
+        tms = torch.tensor([rs["ms_solve"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        xs, ixs, ys = eng.download()
+        tto_se = {"workload": f"{args.workload}: dense LP m={m} n={n}, seed {seed}, slack basis to optimum on {world} GPUs",
+                  "pricing_rule": "steepest edge (Goldfarb-Reid recurrence)", "status": int(rs["status"]),
+                  "pivots": int(rs["pivots"]), "iterations": int(rs["iterations"]), "z": rs["z"],
+                  "seconds": float(tms.item()) * 1e-3, "wall_seconds": wall,
+                  "pivots_per_s": rs["pivots"] / (float(tms.item()) * 1e-3)}
+        if rank == 0:
+            from bench import optimality_certificate
+            tto_se["certificate"] = optimality_certificate(m, n, xs, ixs, ys, rs["z"])
+        dist.barrier()
+
     from bench import bytes_per_pivot, config_for, measured_peak_gbs, parity_fields
     # every rank holds the replicated trace: all of them must carry the digest rank 0 prints
     sha_bytes = torch.tensor(list(bytes.fromhex(parity_fields(args.workload, P, trace, r["z"])["trace_sha256"])),
@@ -124,6 +151,8 @@ def run(args, wl, seed, eps):
         "replicas_agree": replicas_agree, "pivots_timed": int(piv), **parity_fields(args.workload, P, trace, r["z"]),
         "exchange_bytes_per_pivot_per_rank": plan.exchange_bytes_per_pivot(),
     }
+    if tto_se:
+        out["extra"] = {"time_to_optimal_steepest_edge": {args.workload: tto_se}}
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
