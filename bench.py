@@ -128,6 +128,27 @@ def time_to_optimal(name, wl, dev=0, rule=0):
     return out
 
 
+def klee_minty_20(dev=0):
+    """BASELINE config 5a: the Klee-Minty cube of dimension 20 (m=20, n=40, all data exact integers < 2^53) —
+    exactly 2^20 - 1 Dantzig pivots to the optimum 5^20, a pure latency test (simplex_tiny: one CTA, state in shared memory)."""
+    import simplex_method_gpu_b200 as lp
+    d = 20
+    A = np.zeros((d, 2 * d), order="F")
+    for i in range(d):
+        for j in range(i):
+            A[i, j] = 2.0 ** (i - j + 1)
+        A[i, i] = 1.0
+        A[i, d + i] = 1.0
+    b = 5.0 ** np.arange(1, d + 1)
+    c = np.concatenate([2.0 ** np.arange(d - 1, -1, -1), np.zeros(d)])
+    with lp.Engine(d, 2 * d, np.float64, eps=1e-4, max_iter=1 << 40, device=dev) as e:
+        e.upload(A, b, c)
+        r = e.run(1 << 40)
+    return {"workload": "Klee-Minty cube d=20 (m=20, n=40)", "status": int(r["status"]), "pivots": int(r["pivots"]),
+            "expected_pivots": 2 ** d - 1, "z": r["z"], "z_exact": bool(r["z"] == 5.0 ** d), "seconds": r["ms_solve"] * 1e-3,
+            "us_per_pivot": r["ms_solve"] * 1e3 / max(int(r["pivots"]), 1), "kernel": "simplex_tiny<double>"}
+
+
 def optimality_certificate(m, n, x_b, b_ixs, y, z):
     """Solver-independent proof of optimality (GLPK is absent, HiGHS is too slow on a dense 8192 x 8192 LP):
     primal feasibility A_s x <= b, x >= 0, dual feasibility y >= 0, y'A_s >= c_s, and zero duality gap c'x = b'y,
@@ -299,6 +320,8 @@ def run_b200_single(args, wl):
                     piv += sol.pivots
             lp.set_memory_cache(False)
             return {"value": piv / sum(times), "unit": "pivots/s", "ms_per_step": 1e3 * sum(times) / len(times),
+                    "ms_per_step_each": [round(1e3 * t, 1) for t in times],
+                    "value_at_median_step": (piv / len(times)) / float(np.median(times)),
                     "last_ms": {"upload": sol.ms_upload, "solve": sol.ms_solve, "download": sol.ms_download},
                     "trace_sha256": trace_digest(sol.trace)}
         plain, cached = timed_calls(False), timed_calls(True)
@@ -306,7 +329,9 @@ def run_b200_single(args, wl):
         d2h = 8 * m + 4 * m + 8 * P + 64        # x_b, b_ixs, trace, result block
         e2e = {**plain, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "pivots_per_step": P,
                "note": "b200lp_solve_f64 per step with pinned host buffers, memory cache OFF (default): cudaMalloc of all "
-                       "device state, H2D of the LP, the pivots, D2H of x_b / b_ixs / trace and cudaFree inside the timed region"}
+                       "device state, H2D of the LP, the pivots, D2H of x_b / b_ixs / trace and cudaFree inside the timed region; "
+                       "value = pivots / total time (mean step); cudaFree of 16 GB takes 9 ms or ~500 ms from call to call "
+                       "(B200LP_TIMING=1), see ms_per_step_each / value_at_median_step"}
         e2e_cached = {**cached, "note": "same call with b200lp_set_memory_cache(1): device buffers survive between calls"}
         del A_np, A_pin
 
@@ -417,6 +442,8 @@ def reference_workload(args, name, wl, P):
     value = piv / sum(times)
     trace = np.stack([r.trace_p, r.trace_q], axis=1) if len(r.trace_p) else np.zeros((0, 2), np.int32)
     return {"value": value, "unit": "pivots/s", "ms_per_step": 1e3 * sum(times) / len(times),
+            "ms_per_step_each": [round(1e3 * t, 1) for t in times],
+            "value_at_median_step": (piv / len(times)) / float(np.median(times)),
             "config": config_for(name, m, n, P),
             "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -499,6 +526,7 @@ def main():
     ap.add_argument("--tto", default="C2,C3", help="comma list of workloads solved to optimality (time-to-optimal), '' = none")
     ap.add_argument("--tto-se", default="C2,C3,C4", help="workloads solved to optimality with steepest-edge pricing "
                                                          "(options.pricing_rule = 1; a different pivot sequence, same optimum)")
+    ap.add_argument("--no-km", action="store_true", help="skip the Klee-Minty 20 solve (config 5a) under 'extra'")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm: force the CPU port")
     ap.add_argument("--ref-pivots", type=int, default=0)
     args = ap.parse_args()
@@ -535,6 +563,8 @@ def main():
             tto[name] = time_to_optimal(name, WORKLOADS[name], dev)
         for name in [x for x in args.tto_se.split(",") if x]:
             tto_se[name] = time_to_optimal(name, WORKLOADS[name], dev, rule=1)
+        if not args.no_km:
+            extra["klee_minty_20"] = klee_minty_20(dev)
         if tto:
             extra["time_to_optimal"] = tto
         if tto_se:
