@@ -554,6 +554,16 @@ public:
 		const long long m = d.m;
 		std::vector<int> bix((size_t)m);
 		CU(cudaMemcpy(bix.data(), d.b_ixs, m * sizeof(int), cudaMemcpyDeviceToHost));
+		// steepest edge: the weight recurrence of the last pivot may still be pending (it rides in the next pricing pass
+		// and reads row_q and the alpha.alpha slice partials); the replay below reuses both buffers, so keep copies
+		T* keep = nullptr;
+		const size_t keep_n = (size_t)d.ld + (size_t)3 * d.nslice;
+		if (hc.se_pending) {
+			CU(cudaMalloc((void**)&keep, keep_n * sizeof(T)));
+			CU(cudaMemcpyAsync(keep, d.row_q, (size_t)d.ld * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+			CU(cudaMemcpyAsync(keep + d.ld, d.dpart, (size_t)3 * d.nslice * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+		}
+		struct Free { T* p; ~Free() { if (p) cudaFree(p); } } keep_guard{keep};
 		k_identity<T><<<num_sms * 8, 256, 0, stream>>>(d);
 		launches++;
 		hc.pending = 0;
@@ -603,7 +613,11 @@ public:
 		k_copy<T><<<num_sms, 256, 0, stream>>>(d.y, d.acol, m);
 		launches += 4;
 		CU(cudaGetLastError());
-		hc.se_pending = hc.se_pending;    // (steepest-edge weights depend on the basis only: untouched)
+		if (keep) {                       // (the steepest-edge weights themselves depend on the basis only: untouched)
+			CU(cudaMemcpyAsync(d.row_q, keep, (size_t)d.ld * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+			CU(cudaMemcpyAsync(d.dpart, keep + d.ld, (size_t)3 * d.nslice * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+			CU(cudaStreamSynchronize(stream));
+		}
 		CU(push_ctl());
 		if (replayed) *replayed = done;
 		return B200LP_OK;

@@ -172,6 +172,11 @@ def test_refactorisation_rebuilds_the_inverse(oracle, engine_lib):
                 assert e.check_basis()[0] <= 1e-10 * np.abs(x1).max()
                 r = e.run(1 << 20)
                 assert r["status"] == lp.SolveStatus.OptimumFound and abs(r["z"] - full.z) <= 1e-9 * abs(full.z), kw
+                # the rebuilt inverse differs from the product-form one in the last bits only, and a pending steepest-edge
+                # weight recurrence survives the refactorisation: the next pivots are the ones of the undisturbed run
+                plain = lp.solve(A, b, c, eps=1e-9, max_iter=1 << 20, **kw)
+                tr = e.trace()
+                assert np.array_equal(tr[:k + 12], plain.trace[:k + 12]), kw
 
 
 def test_guarded_run_refactorises_on_drift(oracle, engine_lib):
