@@ -831,7 +831,8 @@ private:
 		if (l2_persist_bytes) cudaCtxResetPersistingL2Cache();
 		for (void* p : opened) cudaIpcCloseMemHandle(p);
 		opened.clear();
-		for (void* p : owned) cudaFree(p);
+		// newest first: the allocator gets its blocks back in the reverse order it handed them out
+		for (auto it = owned.rbegin(); it != owned.rend(); ++it) cudaFree(*it);
 		if (hA) cudaFree(hA);
 		owned.clear();
 		if (pinned) cudaFreeHost(pinned);
