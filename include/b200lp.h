@@ -248,6 +248,9 @@ int         b200lp_dense_columns(b200lp_engine* e); /* n - m when the slack bloc
 int64_t     b200lp_bytes_per_pivot(b200lp_engine* e); /* algorithmic bytes: s*(2 m^2 + m (n-m)) */
 const char* b200lp_last_error(void);
 const char* b200lp_version(void);
+/* sizeof(b200lp_options) / sizeof(b200lp_result) of the library build: lets a binding check its mirror of the structs */
+int         b200lp_sizeof_options(void);
+int         b200lp_sizeof_result(void);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ EXPORTS = [
     "b200lp_shard_columns", "b200lp_upload_columns", "b200lp_lpgen_dense_host",
     "b200lp_profile_stamps", "b200lp_profile_names", "b200lp_download_profile", "b200lp_check_basis",
     "b200lp_solve_f64_multi", "b200lp_solve_f32_multi", "b200lp_create_multi", "b200lp_abort",
-    "b200lp_refactor", "b200lp_run_guarded",
+    "b200lp_refactor", "b200lp_run_guarded", "b200lp_sizeof_options", "b200lp_sizeof_result",
     # include/b200lp_io.h
     "b200lp_read_lp", "b200lp_write_lp_text", "b200lp_write_lp_binary", "b200lp_free_problem",
 ]
@@ -120,11 +120,17 @@ def lib() -> C.CDLL:
         "b200lp_free_problem": (None, [C.POINTER(Problem)]),
         "b200lp_last_error": (C.c_char_p, []),
         "b200lp_version": (C.c_char_p, []),
+        "b200lp_sizeof_options": (C.c_int, []),
+        "b200lp_sizeof_result": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
+    if L.b200lp_sizeof_options() != C.sizeof(Options) or L.b200lp_sizeof_result() != C.sizeof(Result):
+        raise ImportError("capi.Options / capi.Result do not mirror include/b200lp.h of the library that was loaded "
+                          f"({C.sizeof(Options)} / {C.sizeof(Result)} bytes here, "
+                          f"{L.b200lp_sizeof_options()} / {L.b200lp_sizeof_result()} in {LIB_PATH}): rebuild")
     _lib = L
     return L
 

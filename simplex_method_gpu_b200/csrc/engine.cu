@@ -236,7 +236,6 @@ public:
 		if (opt.ratio_mode == 2 && (nranks > 1 || opt.mode != 0 || opt.fuse_ratio > 0))
 			return fail(B200LP_ERR_ARG, "the Harris ratio test (ratio_mode = 2) needs the single-GPU persistent kernel with the ratio test as its own phase");
 		d.fuse_ratio = opt.fuse_ratio > 0 ? 1 : 0;    // measured: the per-tile release costs more than the phase it saves
-		d.dbg = 0;
 		return B200LP_OK;
 	}
 
@@ -1580,16 +1579,14 @@ int b200lp_run_guarded(b200lp_engine* e, int64_t iterations, int64_t window, dou
 	NEED(e);
 	if (window <= 0) return fail(B200LP_ERR_ARG, "window must be positive");
 	int64_t left = iterations, nref = 0;
-	b200lp_result r, first;
+	b200lp_result r;
 	std::memset(&r, 0, sizeof(r));
 	double ms = 0;
-	bool have_first = false;
 	while (left > 0) {
 		const int64_t w = std::min(left, window);
 		int rc = e->run_async(w);
 		if (!rc) rc = e->wait(&r);
 		if (rc) return rc;
-		if (!have_first) { first = r; have_first = true; }
 		ms += r.ms_solve;
 		left -= w;
 		if (r.status != B200LP_STATUS_MAX_ITER || r.aborted) break;
@@ -1620,5 +1617,7 @@ int b200lp_dense_columns(b200lp_engine* e) { return e ? (int)e->ns : 0; }
 int64_t b200lp_bytes_per_pivot(b200lp_engine* e) { return e ? e->bytes_per_pivot() : 0; }
 const char* b200lp_last_error(void) { return g_err.c_str(); }
 const char* b200lp_version(void) { return "b200lp 0.2 (sm_100a)"; }
+int b200lp_sizeof_options(void) { return (int)sizeof(b200lp_options); }
+int b200lp_sizeof_result(void) { return (int)sizeof(b200lp_result); }
 
 } // extern "C"

@@ -122,7 +122,6 @@ struct Dev {
 	int rg;                   // row tiles per row group
 	int ngrp;                 // row groups of the local row block
 	int fuse_ratio;           // 1: ratio test per row group inside the update+FTRAN pass; 0: a phase of its own after a barrier
-	int dbg;                  // experiments (options.reserved[0])
 	int fuse_book2;           // 1: the O(m) updates of a pivot ride in the prologue of the next pricing pass (y in shared memory)
 	int price_tail;           // columns at the end of the local block priced one at a time (shorter tail of the pass)
 	double pivot_tol;         // ratio-test eligibility alpha > pivot_tol (0 = the reference's strict test, v4:203)
@@ -859,14 +858,9 @@ template <typename T> __device__ __forceinline__ T* xalpha(const Dev<T>& d, int 
 // tile count of a row group: release at gpu scope (the tile's alpha_part stores, made by other threads of the
 // CTA before a barrier, are visible at L2 before the count is).  A release atom is one MEMBAR.ALL.GPU + ATOM;
 // __threadfence() would be an SC fence plus an L1 invalidation (MEMBAR.SC + ERRBAR + CCTL.IVALL) per tile.
-__device__ __forceinline__ unsigned int post_tile(unsigned int* ctr, int variant) {
+__device__ __forceinline__ unsigned int post_tile(unsigned int* ctr) {
 	unsigned int old;
-	if (variant == 1) {
-		__threadfence();
-		old = atomicAdd(ctr, 1u);
-	} else {
-		asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
-	}
+	asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
 	return old + 1u;
 }
 
@@ -1077,7 +1071,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 		}
 		if (FINISH) {
 			if (prev_grp >= 0) {               // CTA uniform
-				if (post) prev_done = post_tile(&d.grp_done[prev_grp], d.dbg);   // (inactive rows / ragged chunk: the fast path above was not taken)
+				if (post) prev_done = post_tile(&d.grp_done[prev_grp]);   // (inactive rows / ragged chunk: the fast path above was not taken)
 				if (tid == POSTER) {
 					const bool last = prev_done == prev_target;
 					if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }   // acquire side: the group's partials are complete at L2
@@ -1096,7 +1090,7 @@ __device__ void update_ftran_phase(const Dev<T>& d, Smem& sh, unsigned char* dyn
 	if (FINISH && prev_grp >= 0) {             // this CTA's last tile: post and look at once
 		__syncthreads();
 		if (tid == POSTER) {
-			const bool last = post_tile(&d.grp_done[prev_grp], d.dbg) == prev_target;
+			const bool last = post_tile(&d.grp_done[prev_grp]) == prev_target;
 			if (last) { d.grp_done[prev_grp] = 0; __threadfence(); }
 			sh.bc_c = last;
 		}

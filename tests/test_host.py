@@ -23,6 +23,9 @@ def test_library_exports_every_declared_symbol(engine_lib):
     for name in sorted(declared):
         assert hasattr(engine_lib, name), f"{name} declared in b200lp.h but not exported"
     assert declared == set(capi.EXPORTS)
+    # the ctypes mirrors of the two structs have the library's layout size (field order is checked by the option tests)
+    assert engine_lib.b200lp_sizeof_options() == C.sizeof(capi.Options)
+    assert engine_lib.b200lp_sizeof_result() == C.sizeof(capi.Result)
     assert b"sm_100a" in engine_lib.b200lp_version()
 
 

@@ -33,7 +33,6 @@ ap.add_argument("--group-rows", type=int, default=0, help="ratio_group_rows (0 =
 ap.add_argument("--tail", type=int, default=0, help="price_tail: 0 auto, -1 none, else columns")
 ap.add_argument("--fuse", type=int, default=0, help="fuse_book2: 0 auto, -1 off")
 ap.add_argument("--fuse-ratio", type=int, default=0, help="fuse_ratio: 0 auto, -1 off")
-ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--rule", type=int, default=0, help="pricing_rule: 0 Dantzig, 1 steepest edge")
 ap.add_argument("--resident", type=int, default=0, help="1: label the stamps of the shared-memory-resident kernel (mid-size LPs, auto configuration)")
 ap.add_argument("--out", default="")
