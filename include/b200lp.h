@@ -69,8 +69,8 @@ typedef struct {
 	int32_t ratio_group_rows; /* rows of B^-1 whose ratio test runs as one unit inside the update+FTRAN pass: 0 = auto (256) */
 	double  pivot_tol;    /* ratio-test eligibility alpha > pivot_tol; 0 (default) = the reference's strict test (v4:203) */
 	int32_t price_tail;   /* columns at the end of a pricing pass handed out one at a time: 0 = auto, -1 = none, else count */
-	int32_t fuse_book2;   /* x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass (3 grid barriers per
-	                         pivot instead of 4): 0 = auto (when y fits in shared memory), -1 = off */
+	int32_t fuse_book2;   /* x_b / y / c_b / b_ixs updates in the prologue of the next pricing pass (4 grid barriers per
+	                         pivot instead of 5): 0 = auto (when y fits in shared memory), -1 = off */
 	int32_t fuse_ratio;   /* ratio test of every row group inside the update+FTRAN pass as the group completes:
 	                         0 = auto (off: measured slower), 1 = on, -1 = off (the ratio test is a
 	                         phase of its own after a grid barrier) */
