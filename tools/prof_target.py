@@ -30,9 +30,14 @@ if a.general:
 if a.emu > 1:
     kw["devices"] = [0] * a.emu
 if a.km:
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import oracle  # test infrastructure: only the LP generator is used here
-    A, b, c = oracle.gen_klee_minty(a.km)
+    dk = a.km                                  # Klee-Minty cube (BASELINE config 5a), all data exact integers
+    A = np.zeros((dk, 2 * dk), order="F")
+    for i in range(dk):
+        for j in range(i):
+            A[i, j] = 2.0 ** (i - j + 1)
+        A[i, i] = A[i, dk + i] = 1.0
+    b = 5.0 ** np.arange(1, dk + 1)
+    c = np.concatenate([2.0 ** np.arange(dk - 1, -1, -1), np.zeros(dk)])
     m, n = A.shape
     kw["eps"] = 1e-4
     e = lp.Engine(m, n, np.float64, **kw)
